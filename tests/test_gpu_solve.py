@@ -1,0 +1,123 @@
+"""GPU parity: the on-device Dopri5 loop (sample / sample+log q / log-prob) vs the oracle's restated diffrax."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ecnf_oracle as O
+from ecnf_b200 import lib as L
+from ecnf_b200.engine import Engine
+from helpers import CASES, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # north-star tolerance on samples and log q (relative)
+
+
+def _setup(case, B, seed=5):
+    n, dim, blocks, units, H, nfeat = CASES[case]
+    ocfg, flat, tree, ecfg = make_pair(n, dim, blocks, units, H, n_features=nfeat)
+    eng = Engine(ecfg)
+    rng = np.random.default_rng(seed)
+    eps = rng.standard_normal((B, n * dim)).astype(np.float32)
+    feat = rng.integers(0, nfeat, (B, n)).astype(np.int32)
+    x0 = O.base_sample_from_noise(ocfg, torch.tensor(eps))
+    return ocfg, flat, tree, eng, x0, feat
+
+
+@pytest.mark.parametrize("case", ["small_64_32", "dw4", "lj13"])
+def test_fixed_step_sample_logq_matches_oracle(case, cuda_device):
+    B = 3 if case == "lj13" else 6
+    ocfg, flat, tree, eng, x0, feat = _setup(case, B)
+    ctrl_o = O.SolveControl(fixed=True, step_size=0.05)
+    p32 = O.to_torch(flat, torch.float32)
+    x1_ref, logq_ref, st_ref = O.sample_and_log_prob_cnf(p32, ocfg, x0, torch.tensor(feat).long(), ctrl_o)
+    x1, logs, stats = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, L.make_ctrl(use_fixed_step_size=True))
+    stats = stats.cpu().numpy()
+    assert (stats[:, 0] == 20).all() and (stats[:, 1] == 20).all() and (stats[:, 2] == 121).all()
+    assert (stats[:, 0] == st_ref.n_steps).all() and (stats[:, 2] == st_ref.n_evals).all()
+    assert rel_err(x1.cpu().numpy(), x1_ref.numpy()) < TOL
+    logs = logs.cpu().numpy()
+    assert np.abs(logs[:, 0] - logq_ref.numpy()).max() < TOL * (np.abs(logq_ref.numpy()).max() + 1)
+    # round trip: log-prob of the samples integrates back to the base draw (core_test.py:42-43)
+    xb, logs_b, _ = eng.solve(tree, L.MODE_LOGPROB, x1, feat, L.make_ctrl(use_fixed_step_size=True))
+    assert np.abs(xb.cpu().numpy() - x0.numpy()).max() < 2e-2  # dt=0.05 truncation error, not a parity bound
+    assert np.abs(logs_b.cpu().numpy()[:, 0] - logs[:, 0]).max() < 2e-2 * (np.abs(logs[:, 0]).max() + 1)
+
+
+def _setup_v(case, B, seed, head_variance, zero_time=False):
+    n, dim, blocks, units, H, nfeat = CASES[case]
+    ocfg, flat, tree, ecfg = make_pair(n, dim, blocks, units, H, n_features=nfeat, head_variance=head_variance,
+                                       zero_time=zero_time)
+    eng = Engine(ecfg)
+    rng = np.random.default_rng(seed)
+    eps = rng.standard_normal((B, n * dim)).astype(np.float32)
+    feat = rng.integers(0, nfeat, (B, n)).astype(np.int32)
+    return ocfg, flat, tree, eng, O.base_sample_from_noise(ocfg, torch.tensor(eps)), feat
+
+
+@pytest.mark.parametrize("case", ["small_64_32", "dw4"])
+def test_adaptive_matches_oracle_smooth_field(case, cuda_device):
+    """Adaptive Dopri5 + I-controller on an autonomous field (time-embedding rows zeroed, so no sin(1000 t) forcing
+    and a non-chaotic step sequence): same step sequence (up to an accept/reject flip when scaled_err ~ 1),
+    samples / log q / get_log_prob within 1e-4."""
+    B = 6
+    ocfg, flat, tree, eng, x0, feat = _setup_v(case, B, 7, 0.3, zero_time=True)
+    p32 = O.to_torch(flat, torch.float32)
+    ctrl_o = O.SolveControl()
+    x1_ref, logq_ref, st_ref = O.sample_and_log_prob_cnf(p32, ocfg, x0, torch.tensor(feat).long(), ctrl_o)
+    x1, logs, stats = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, L.make_ctrl())
+    stats = stats.cpu().numpy()
+    assert (stats[:, 3] == 0).all()
+    print("adaptive steps cuda", stats[:, 0], stats[:, 1], "oracle", st_ref.n_steps, st_ref.n_accepted)
+    assert np.abs(stats[:, 0] - st_ref.n_steps).max() <= 1, (stats[:, 0], st_ref.n_steps)
+    assert np.abs(stats[:, 1] - st_ref.n_accepted).max() <= 1, (stats[:, 1], st_ref.n_accepted)
+    assert rel_err(x1.cpu().numpy(), x1_ref.numpy()) < TOL
+    assert np.abs(logs.cpu().numpy()[:, 0] - logq_ref.numpy()).max() < TOL * (np.abs(logq_ref.numpy()).max() + 1)
+    lp_ref, lpb_ref, dl_ref, _ = O.get_log_prob(p32, ocfg, x1_ref, torch.tensor(feat).long(), ctrl_o)
+    xb, logs_b, _ = eng.solve(tree, L.MODE_LOGPROB, x1_ref.numpy(), feat, L.make_ctrl())
+    lb = logs_b.cpu().numpy()
+    for k, ref in enumerate((lp_ref, lpb_ref, dl_ref)):
+        assert np.abs(lb[:, k] - ref.numpy()).max() < TOL * (np.abs(ref.numpy()).max() + 1)
+
+
+def test_adaptive_stiff_field_within_solver_tolerance(cuda_device):
+    """On the 'stiffened' O(1) field (fast sin(1000 t) forcing, ~140 steps, many rejections) two fp32 solvers
+    follow different accept/reject sequences, so parity is 'within ODE tolerance': the CUDA result must be as close
+    to a tight fp64 solution as the fp32 oracle is (x3 slack)."""
+    B = 4
+    ocfg, flat, tree, eng, x0, feat = _setup_v("dw4", B, 7, 1.0)
+    ft = torch.tensor(feat).long()
+    x1_32, lq_32, st32 = O.sample_and_log_prob_cnf(O.to_torch(flat, torch.float32), ocfg, x0, ft, O.SolveControl())
+    x1_64, lq_64, _ = O.sample_and_log_prob_cnf(O.to_torch(flat, torch.float64), ocfg, x0.double(), ft,
+                                                 O.SolveControl(rtol=1e-9, atol=1e-9))
+    x1, logs, stats = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, L.make_ctrl())
+    e_o = np.abs(x1_32.numpy() - x1_64.numpy()).max()
+    e_c = np.abs(x1.cpu().numpy() - x1_64.numpy()).max()
+    assert e_c < 3 * e_o + 1e-4, (e_c, e_o)
+    l_o = np.abs(lq_32.numpy() - lq_64.numpy()).max()
+    l_c = np.abs(logs.cpu().numpy()[:, 0] - lq_64.numpy()).max()
+    assert l_c < 3 * l_o + 1e-3, (l_c, l_o)
+    n_c, n_o = stats.cpu().numpy()[:, 0], st32.n_steps
+    assert np.abs(n_c - n_o).max() < 0.25 * n_o.max(), (n_c, n_o)
+
+
+def test_sample_only_matches_oracle(cuda_device):
+    ocfg, flat, tree, eng, x0, feat = _setup("dw4", 8, seed=9)
+    p32 = O.to_torch(flat, torch.float32)
+    ocfg, flat, tree, eng, x0, feat = _setup_v("dw4", 8, 9, 0.3, zero_time=True)
+    p32 = O.to_torch(flat, torch.float32)
+    for fixed in (True, False):
+        x1_ref, st = O.sample_cnf(p32, ocfg, x0, torch.tensor(feat).long(), O.SolveControl(fixed=fixed))
+        x1, _, stats = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, L.make_ctrl(use_fixed_step_size=fixed))
+        assert rel_err(x1.cpu().numpy(), x1_ref.numpy()) < TOL
+        if fixed:
+            assert (stats.cpu().numpy()[:, 2] == 121).all()
+
+
+def test_max_steps_status(cuda_device):
+    ocfg, flat, tree, eng, x0, feat = _setup("dw4", 2)
+    _, _, stats = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, L.make_ctrl(max_steps=3))
+    st = stats.cpu().numpy()
+    assert (st[:, 3] == 1).all() and (st[:, 0] == 3).all()
