@@ -222,15 +222,23 @@ def egnn_apply(p: Dict[str, torch.Tensor], cfg: CnfConfig, x: torch.Tensor, t: t
     return out.reshape(B, n * dim)
 
 
-def vf_and_exact_div(p, cfg: CnfConfig, x: torch.Tensor, t: torch.Tensor, feat: torch.Tensor):
-    """(f, tr df/dx) with the Jacobian built row by row in REVERSE mode, like
-    ``jax.vmap(vjp_fn)(eye)`` + ``jnp.trace`` (sample_and_log_prob.py:64-66).  Independent of the CUDA
-    kernel's forward-mode formulation on purpose."""
+def vf_and_exact_div(p, cfg: CnfConfig, x: torch.Tensor, t: torch.Tensor, feat: torch.Tensor, batched: bool = False):
+    """(f, tr df/dx) with the full Jacobian built in REVERSE mode from the D one-hot cotangents, like
+    ``jax.vmap(vjp_fn)(jnp.eye(D))`` + ``jnp.trace`` (sample_and_log_prob.py:64-66).  Independent of the CUDA
+    kernel's forward-mode formulation on purpose.  ``batched=True`` pushes the D cotangents through one
+    vectorised backward pass (what vmap does); ``batched=False`` loops over them, which torch runs faster on
+    the CPU for B >= 8 and is therefore the default (and what the CPU baseline times)."""
     xg = x.detach().clone().requires_grad_(True)
     f = egnn_apply(p, cfg, xg, t, feat)
-    div = torch.zeros(x.shape[0], dtype=x.dtype)
-    for d in range(f.shape[1]):
-        (g,) = torch.autograd.grad(f[:, d].sum(), xg, retain_graph=d + 1 < f.shape[1])
+    B, D = f.shape
+    if batched:
+        eye = torch.eye(D, dtype=f.dtype)[:, None, :].expand(D, B, D)
+        (jac,) = torch.autograd.grad(f, xg, grad_outputs=eye, is_grads_batched=True)   # [D(out), B, D(in)]
+        div = torch.diagonal(jac.permute(1, 0, 2), dim1=1, dim2=2).sum(dim=1)
+        return f.detach(), div
+    div = torch.zeros(B, dtype=x.dtype)
+    for d in range(D):
+        (g,) = torch.autograd.grad(f[:, d].sum(), xg, retain_graph=d + 1 < D)
         div = div + g[:, d]
     return f.detach(), div
 
