@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-diag-suppress", "177",
 ]
+if os.environ.get("ECNF_TC_PROFILE"):      # per-phase cycle counters in the tensor-core kernel (tools/tc_profile.py)
+    NVCC_FLAGS.append("-DECNF_TC_PROFILE")
 
 
 def _nvcc() -> str:

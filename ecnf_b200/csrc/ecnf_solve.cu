@@ -23,6 +23,16 @@ int grid_for(const ecnf_model* m, int64_t B) {
   return (int)g;
 }
 
+int g_engine = 0;   // 0 = auto (tensor cores where eligible), 1 = force the fp32 SIMT engine
+
+bool use_tc(const ecnf_model* m, bool div) {
+  return g_engine == 0 && tc_eligible(m, div);
+}
+
+int64_t scratch_stride_of(const ecnf_model* m, bool div) {
+  return (scratch_floats(m->cfg.n_frames, m->cfg.dim, m->cfg.n_hidden, m->cfg.mlp_units, div) + 63) & ~63LL;
+}
+
 bool mode_div(int mode) { return mode == ECNF_MODE_VF_DIV || mode == ECNF_MODE_SAMPLE_LOGQ || mode == ECNF_MODE_LOGPROB; }
 
 int run(const ecnf_model* m, int mode, const float* x, const float* t, const int32_t* feat, int64_t B,
@@ -55,8 +65,13 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
   a.out_stats = out_stats;
   a.counter = reinterpret_cast<unsigned int*>(ws);
   a.scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256);
-  a.scratch_stride = (scratch_floats(m->cfg.n_frames, m->cfg.dim, m->cfg.n_hidden, m->cfg.mlp_units, div) + 63) & ~63LL;
+  a.scratch_stride = scratch_stride_of(m, div);
+  a.img.base = nullptr;
   ECNF_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+  if (use_tc(m, div)) {
+    void* image_ws = reinterpret_cast<char*>(ws) + 256 + (int64_t)grid * a.scratch_stride * (int64_t)sizeof(float);
+    return launch_tc(m, a, grid, image_ws, st);
+  }
   return div ? launch_uh<true>(m, a, grid, st) : launch_uh<false>(m, a, grid, st);
 }
 
@@ -67,8 +82,14 @@ extern "C" {
 int64_t ecnf_solve_workspace_bytes(const ecnf_model* m, int mode, int64_t B) {
   if (!m) return 0;
   const bool div = mode_div(mode);
-  const int64_t stride = (scratch_floats(m->cfg.n_frames, m->cfg.dim, m->cfg.n_hidden, m->cfg.mlp_units, div) + 63) & ~63LL;
-  return 256 + (int64_t)grid_for(m, B < 1 ? 1 : B) * stride * (int64_t)sizeof(float);
+  const int64_t stride = scratch_stride_of(m, div);
+  return 256 + (int64_t)grid_for(m, B < 1 ? 1 : B) * stride * (int64_t)sizeof(float) + (tc_eligible(m, div) ? tc_image_bytes(m) : 0);
+}
+
+int ecnf_set_engine(int engine) {
+  if (engine != 0 && engine != 1) { ecnf_set_error("ecnf_set_engine: 0 = auto, 1 = fp32 SIMT"); return ECNF_ERR_INVALID; }
+  g_engine = engine;
+  return ECNF_OK;
 }
 
 int ecnf_vf_forward(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, int64_t B, float* out_f,

@@ -10,6 +10,21 @@ __host__ __device__ inline int64_t scratch_floats(int n, int dim, int H, int U, 
   return n * ND * (2 * (int64_t)H + 3 * (int64_t)U);
 }
 
+// byte offsets of the bf16 (hi, lo) weight images used by the tensor-core engine (ecnf_solve_tc.cuh)
+struct TcImgBlock {
+  int Wd, We0s, We0r, We[ECNF_MAX_LAYERS], Wx[ECNF_MAX_LAYERS], Wh0m, Wh0h, Wh[ECNF_MAX_LAYERS], WhL;
+};
+struct TcImages {
+  const unsigned char* base;
+  TcImgBlock blk[ECNF_MAX_BLOCKS];
+};
+
+// shared-memory carve-up of the tensor-core engine (byte offsets), computed on the host
+struct TcSmemLayout {
+  int Wb0, Wb1, stage, G, macc, vecs, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, rowsd, rowslot, rowgrp, rdot, gi, gj,
+      giz, gv, gs1, glen, ginv, ge, bars, prof, total_bytes;
+};
+
 struct KernelArgs {
   EcnfModelDev m;
   int mode;
@@ -24,9 +39,16 @@ struct KernelArgs {
   float* scratch;        // per-CTA global scratch
   long long scratch_stride;
   unsigned int* counter;
+  TcImages img;
+  TcSmemLayout lay;
 };
 
 template <int U, int H, bool DIV>
 int launch_t(const ecnf_model* mdl, KernelArgs& a, int grid, cudaStream_t st);
+
+// tensor-core engine (U = 128, H = 64, exact divergence): eligibility, extra workspace, launch
+bool tc_eligible(const ecnf_model* mdl, bool div);
+int64_t tc_image_bytes(const ecnf_model* mdl);
+int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cudaStream_t st);
 
 }  // namespace ecnf_solve_detail

@@ -230,6 +230,9 @@ struct Engine {
     Mg = Pr + (size_t)n * ND * U;
   }
 
+  __device__ __forceinline__ float* ode_ptr() const { return ode; }
+  __device__ __forceinline__ float* red_ptr() const { return red; }
+
   // rowdot[row] = sum_col X[row][col] * vec[col]   (one warp per row)
   __device__ void rowdot_tile(const float* X, const float* __restrict__ vec, int nrows) {
     const int warp = tid >> 5, lane = tid & 31;
@@ -585,20 +588,60 @@ __device__ __forceinline__ float clip_to_end(float tprev, float tnext, float T1,
   return tnext;
 }
 
-template <int U, int H, bool DIV>
-__global__ void __launch_bounds__(NTHREADS, 1) ecnf_solve_kernel(const __grid_constant__ KernelArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  __shared__ long long s_traj;
-  __shared__ float s_ctl[8];
-  Engine<U, H, DIV> eng(a.m, smem, a.scratch + (size_t)blockIdx.x * a.scratch_stride);
+// The ODE driver (diffrax.diffeqsolve restated), generic over the engine that evaluates the vector field.
+// Written as a state machine around ONE call site of eng.eval so that the (large) evaluation code is inlined exactly
+// once and the engine's state stays in registers.
+template <class Eng, bool DIV>
+__device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long long& s_traj, float* s_ctl) {
   const int tid = threadIdx.x;
   const int D = eng.D, S = DIV ? D + 1 : D;
-  float* y = eng.ode;          // [S]
+  float* y = eng.ode_ptr();    // [S]
   float* ys = y + S;           // [S] stage input
   float* f0 = ys + S;          // [S] FSAL derivative (direction applied)
   float* fo = f0 + S;          // [S] eval output
   float* kk = fo + S;          // [7][S]
-  float* red = eng.red;
+  float* red = eng.red_ptr();
+  const ecnf_solve_ctrl& c = a.ctrl;
+  const bool vf_mode = (a.mode == ECNF_MODE_VF || a.mode == ECNF_MODE_VF_DIV);
+  const bool reverse = (a.mode == ECNF_MODE_LOGPROB);
+  const float dir = reverse ? -1.f : 1.f;
+  const float T0 = reverse ? -1.f : 0.f, T1 = reverse ? 0.f : 1.f;  // internal (direction-multiplied) times
+  enum { PH_VF = 0, PH_F0 = 1, PH_F1 = 2, PH_STAGE = 3 };
+
+  auto rms_of_red = [&]() -> float {  // sqrt(mean(red[0..S)^2)), result broadcast to all threads
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int i = 0; i < S; ++i) s = fmaf(red[i], red[i], s);
+      s_ctl[0] = sqrtf(s / (float)S);
+    }
+    __syncthreads();
+    const float r = s_ctl[0];
+    __syncthreads();
+    return r;
+  };
+  // log p0 of the D positions in v (zero_com_base.py:44-47,64-84 + ildj), computed by thread 0, broadcast
+  auto base_logp = [&](const float* v) -> float {
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int cdim = 0; cdim < eng.dim; ++cdim) {
+        float mean = 0.f;
+        for (int i = 0; i < eng.n; ++i) mean += v[i * eng.dim + cdim] / a.m.base_scale;
+        mean /= (float)eng.n;
+        for (int i = 0; i < eng.n; ++i) {
+          const float z = v[i * eng.dim + cdim] / a.m.base_scale - mean;
+          s = fmaf(z, z, s);
+        }
+      }
+      const float dof = (float)((eng.n - 1) * eng.dim);
+      s_ctl[1] = -0.5f * s - 0.5f * dof * 1.8378770664093453f - dof * logf(a.m.base_scale);
+    }
+    __syncthreads();
+    const float r = s_ctl[1];
+    __syncthreads();
+    return r;
+  };
 
   for (;;) {
     if (tid == 0) s_traj = (long long)atomicAdd(a.counter, 1u);
@@ -609,152 +652,138 @@ __global__ void __launch_bounds__(NTHREADS, 1) ecnf_solve_kernel(const __grid_co
     const int32_t* feat = a.feat + b * eng.n;
     const float* xin = a.x_init + b * D;
 
-    if (a.mode == ECNF_MODE_VF || a.mode == ECNF_MODE_VF_DIV) {
-      for (int i = tid; i < D; i += NTHREADS) ys[i] = xin[i];
-      __syncthreads();
-      eng.eval(a.t_in[b], ys, feat, fo);
-      for (int i = tid; i < D; i += NTHREADS) a.out_x[b * D + i] = fo[i];
-      if (DIV && tid == 0) a.out_logs[b] = fo[D];
-      __syncthreads();
-      continue;
-    }
-
-    const bool reverse = (a.mode == ECNF_MODE_LOGPROB);
-    const float dir = reverse ? -1.f : 1.f;
-    const float T0 = reverse ? -1.f : 0.f, T1 = reverse ? 0.f : 1.f;  // internal (direction-multiplied) times
-    const ecnf_solve_ctrl& c = a.ctrl;
-    int n_steps = 0, n_acc = 0, n_evals = 0;
-
-    for (int i = tid; i < S; i += NTHREADS) y[i] = (i < D) ? xin[i] : 0.f;
-    __syncthreads();
-    float lp0_start = 0.f;
-    // F(tau, yin) = dir * f(dir * tau, yin)
-    auto F = [&](float tau_, const float* yin, float* out) {
-      eng.eval(dir * tau_, yin, feat, fo);
-      for (int i = tid; i < S; i += NTHREADS) out[i] = dir * fo[i];
-      __syncthreads();
-      ++n_evals;
-    };
-    auto rms_of_red = [&]() -> float {  // sqrt(mean(red[0..S)^2)), result broadcast to all threads
-      __syncthreads();
-      if (tid == 0) {
-        float s = 0.f;
-        for (int i = 0; i < S; ++i) s = fmaf(red[i], red[i], s);
-        s_ctl[0] = sqrtf(s / (float)S);
-      }
-      __syncthreads();
-      const float r = s_ctl[0];
-      __syncthreads();
-      return r;
-    };
-
-    float tprev = T0;
-    F(tprev, y, f0);
-    float dt0;
-    if (c.fixed) {
-      dt0 = fabsf(c.step_size);
-    } else {
-      // Hairer-Wanner initial step (diffrax _select_initial_step)
-      for (int i = tid; i < S; i += NTHREADS) red[i] = y[i] / (c.atol + fabsf(y[i]) * c.rtol);
-      const float d0 = rms_of_red();
-      for (int i = tid; i < S; i += NTHREADS) red[i] = f0[i] / (c.atol + fabsf(y[i]) * c.rtol);
-      const float d1 = rms_of_red();
-      const bool cond = (d0 < 1e-5f) || (d1 < 1e-5f);
-      const float h0 = cond ? 1e-6f : 0.01f * d0 / d1;
-      for (int i = tid; i < S; i += NTHREADS) ys[i] = y[i] + h0 * f0[i];
-      __syncthreads();
-      F(tprev + h0, ys, kk);  // f1 into kk[0]
-      for (int i = tid; i < S; i += NTHREADS) red[i] = (kk[i] - f0[i]) / (c.atol + fabsf(y[i]) * c.rtol);
-      const float d2 = rms_of_red() / h0;
-      const float md = fmaxf(d1, d2);
-      const float h1 = (md <= 1e-15f) ? fmaxf(1e-6f, h0 * 1e-3f) : powf(0.01f / md, 1.f / c.error_order);
-      dt0 = fmaxf(fminf(100.f * h0, h1), c.dtmin);
-    }
-    float tnext = clip_to_end(tprev, tprev + dt0, T1, true);
+    int phase, stage = 0, n_steps = 0, n_acc = 0, n_evals = 0, status = 0;
+    float tprev = T0, tnext = T0, dt = 0.f, h0 = 0.f, d1 = 0.f, t_eval, lp0_start = 0.f;
     bool at_dtmin = false;
-    int status = 0;
-    if (DIV && !reverse) {
-      // log p0(x0) of the starting point (sample_and_log_prob.py:147)
-      if (tid == 0) {
-        float s = 0.f;
-        for (int cdim = 0; cdim < eng.dim; ++cdim) {
-          float mean = 0.f;
-          for (int i = 0; i < eng.n; ++i) mean += y[i * eng.dim + cdim] / a.m.base_scale;
-          mean /= (float)eng.n;
-          for (int i = 0; i < eng.n; ++i) {
-            const float z = y[i * eng.dim + cdim] / a.m.base_scale - mean;
-            s = fmaf(z, z, s);
-          }
-        }
-        const float dof = (float)((eng.n - 1) * eng.dim);
-        s_ctl[1] = -0.5f * s - 0.5f * dof * 1.8378770664093453f - dof * logf(a.m.base_scale);
-      }
-      __syncthreads();
-      lp0_start = s_ctl[1];
+    const float* ein;
+    if (vf_mode) {
+      for (int i = tid; i < D; i += NTHREADS) ys[i] = xin[i];
+      phase = PH_VF;
+      t_eval = a.t_in[b];
+      ein = ys;
+    } else {
+      for (int i = tid; i < S; i += NTHREADS) y[i] = (i < D) ? xin[i] : 0.f;
+      phase = PH_F0;
+      t_eval = dir * T0;
+      ein = y;
     }
+    __syncthreads();
+    if (DIV && !vf_mode && !reverse) lp0_start = base_logp(y);   // log p0(x0), sample_and_log_prob.py:147
 
-    while (tprev < T1) {
-      if (n_steps >= c.max_steps) { status = 1; break; }
-      const float dt = tnext - tprev;
-      for (int i = tid; i < S; i += NTHREADS) kk[i] = f0[i] * dt;
-      __syncthreads();
-      for (int s = 1; s < 7; ++s) {
+    bool running = true;
+    while (running) {
+      eng.eval(t_eval, ein, feat, fo);      // fo[0..D) = f, fo[D] = div f  -- the single evaluation site
+      ++n_evals;
+      bool begin_step = false;
+      if (phase == PH_VF) {
+        for (int i = tid; i < D; i += NTHREADS) a.out_x[b * D + i] = fo[i];
+        if (DIV && tid == 0) a.out_logs[b] = fo[D];
+        running = false;
+      } else if (phase == PH_F0) {
+        // F(tau, y) = dir * f(dir * tau, y); FSAL initialisation
+        for (int i = tid; i < S; i += NTHREADS) f0[i] = dir * fo[i];
+        __syncthreads();
+        if (c.fixed) {
+          tnext = clip_to_end(tprev, tprev + fabsf(c.step_size), T1, true);
+          begin_step = true;
+        } else {
+          // Hairer-Wanner initial step (diffrax _select_initial_step)
+          for (int i = tid; i < S; i += NTHREADS) red[i] = y[i] / (c.atol + fabsf(y[i]) * c.rtol);
+          const float d0 = rms_of_red();
+          for (int i = tid; i < S; i += NTHREADS) red[i] = f0[i] / (c.atol + fabsf(y[i]) * c.rtol);
+          d1 = rms_of_red();
+          const bool cond = (d0 < 1e-5f) || (d1 < 1e-5f);
+          h0 = cond ? 1e-6f : 0.01f * d0 / d1;
+          for (int i = tid; i < S; i += NTHREADS) ys[i] = y[i] + h0 * f0[i];
+          __syncthreads();
+          t_eval = dir * (tprev + h0);
+          ein = ys;
+          phase = PH_F1;
+        }
+      } else if (phase == PH_F1) {
+        for (int i = tid; i < S; i += NTHREADS) red[i] = (dir * fo[i] - f0[i]) / (c.atol + fabsf(y[i]) * c.rtol);
+        const float d2 = rms_of_red() / h0;
+        const float md = fmaxf(d1, d2);
+        const float h1 = (md <= 1e-15f) ? fmaxf(1e-6f, h0 * 1e-3f) : powf(0.01f / md, 1.f / c.error_order);
+        const float dt0 = fmaxf(fminf(100.f * h0, h1), c.dtmin);
+        tnext = clip_to_end(tprev, tprev + dt0, T1, true);
+        begin_step = true;
+      } else {  // PH_STAGE: stage `stage` (1..6) of the current step has just been evaluated at ys
+        for (int i = tid; i < S; i += NTHREADS) kk[stage * S + i] = (dir * fo[i]) * dt;
+        __syncthreads();
+        if (stage < 6) {
+          ++stage;
+        } else {
+          // ys holds the 5th-order solution y1; dir * fo = F(t + dt, y1) is next step's first stage (FSAL)
+          bool keep = true;
+          float new_prev, new_next;
+          if (c.fixed) {
+            new_prev = tnext;
+            new_next = tnext + dt;
+          } else {
+            for (int i = tid; i < S; i += NTHREADS) {
+              float e = 0.f;
+              for (int j = 0; j < 7; ++j) {
+                const float bj = c_BERR[j];
+                if (bj != 0.f) e = e + bj * kk[j * S + i];
+              }
+              red[i] = e / (c.atol + fmaxf(fabsf(y[i]), fabsf(ys[i])) * c.rtol);
+            }
+            const float err = rms_of_red();
+            keep = (err < 1.f) || at_dtmin;
+            const float inv = (err == 0.f) ? INFINITY : 1.f / err;
+            float factor = c.safety * powf(inv, 1.f / c.error_order);
+            const float fmin_ = keep ? 1.f : c.factormin;
+            factor = fminf(fmaxf(factor, fmin_), c.factormax);
+            float ndt = dt * factor;
+            at_dtmin = ndt <= c.dtmin;
+            ndt = fmaxf(ndt, c.dtmin);
+            new_prev = keep ? tnext : tprev;
+            new_next = new_prev + ndt;
+          }
+          new_prev = fminf(new_prev, T1);
+          new_next = clip_to_end(new_prev, new_next, T1, keep);
+          if (keep) {
+            for (int i = tid; i < S; i += NTHREADS) { y[i] = ys[i]; f0[i] = dir * fo[i]; }
+            ++n_acc;
+          }
+          __syncthreads();
+          tprev = new_prev;
+          tnext = new_next;
+          ++n_steps;
+          if (!(tprev < T1)) running = false;
+          else if (n_steps >= c.max_steps) { status = 1; running = false; }
+          else begin_step = true;
+        }
+      }
+      if (begin_step) {
+        dt = tnext - tprev;
+        for (int i = tid; i < S; i += NTHREADS) kk[i] = f0[i] * dt;
+        __syncthreads();
+        stage = 1;
+        phase = PH_STAGE;
+        if (c.max_steps <= 0) { status = 1; running = false; }
+      }
+      if (running && phase == PH_STAGE) {
+        // stage input: ys = y + sum_j a[stage][j] k_j ; time tprev + c[stage] dt
         for (int i = tid; i < S; i += NTHREADS) {
           float v = y[i];
-          for (int j = 0; j < s; ++j) {
-            const float aj = c_A[s][j];
+          for (int j = 0; j < stage; ++j) {
+            const float aj = c_A[stage][j];
             if (aj != 0.f) v = v + aj * kk[j * S + i];
           }
           ys[i] = v;
         }
         __syncthreads();
-        F(tprev + c_C[s] * dt, ys, kk + s * S);
-        // keep raw derivative of the last stage for FSAL, then scale by dt
-        if (s == 6)
-          for (int i = tid; i < S; i += NTHREADS) fo[i] = kk[s * S + i];
-        for (int i = tid; i < S; i += NTHREADS) kk[s * S + i] *= dt;
-        __syncthreads();
+        t_eval = dir * (tprev + c_C[stage] * dt);
+        ein = ys;
       }
-      // ys now holds the 5th-order solution y1; fo holds F(t+dt, y1)
-      bool keep = true;
-      float new_prev, new_next;
-      if (c.fixed) {
-        new_prev = tnext;
-        new_next = tnext + dt;
-      } else {
-        for (int i = tid; i < S; i += NTHREADS) {
-          float e = 0.f;
-          for (int j = 0; j < 7; ++j) {
-            const float bj = c_BERR[j];
-            if (bj != 0.f) e = e + bj * kk[j * S + i];
-          }
-          red[i] = e / (c.atol + fmaxf(fabsf(y[i]), fabsf(ys[i])) * c.rtol);
-        }
-        const float err = rms_of_red();
-        keep = (err < 1.f) || at_dtmin;
-        const float inv = (err == 0.f) ? INFINITY : 1.f / err;
-        float factor = c.safety * powf(inv, 1.f / c.error_order);
-        const float fmin_ = keep ? 1.f : c.factormin;
-        factor = fminf(fmaxf(factor, fmin_), c.factormax);
-        float ndt = dt * factor;
-        at_dtmin = ndt <= c.dtmin;
-        ndt = fmaxf(ndt, c.dtmin);
-        new_prev = keep ? tnext : tprev;
-        new_next = new_prev + ndt;
-      }
-      new_prev = fminf(new_prev, T1);
-      new_next = clip_to_end(new_prev, new_next, T1, keep);
-      if (keep) {
-        for (int i = tid; i < S; i += NTHREADS) { y[i] = ys[i]; f0[i] = fo[i]; }
-        ++n_acc;
-      }
-      __syncthreads();
-      tprev = new_prev;
-      tnext = new_next;
-      ++n_steps;
     }
+    if (vf_mode) { __syncthreads(); continue; }
 
     for (int i = tid; i < D; i += NTHREADS) a.out_x[b * D + i] = y[i];
+    float lpb_end = 0.f;
+    if (DIV && reverse) lpb_end = base_logp(y);
     if (tid == 0) {
       if (a.out_stats) {
         a.out_stats[b * 4 + 0] = n_steps; a.out_stats[b * 4 + 1] = n_acc;
@@ -767,26 +796,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) ecnf_solve_kernel(const __grid_co
           a.out_logs[b * 3 + 1] = lp0_start;
           a.out_logs[b * 3 + 2] = delta;
         } else {
-          float s = 0.f;
-          for (int cdim = 0; cdim < eng.dim; ++cdim) {
-            float mean = 0.f;
-            for (int i = 0; i < eng.n; ++i) mean += y[i * eng.dim + cdim] / a.m.base_scale;
-            mean /= (float)eng.n;
-            for (int i = 0; i < eng.n; ++i) {
-              const float z = y[i * eng.dim + cdim] / a.m.base_scale - mean;
-              s = fmaf(z, z, s);
-            }
-          }
-          const float dof = (float)((eng.n - 1) * eng.dim);
-          const float lpb = -0.5f * s - 0.5f * dof * 1.8378770664093453f - dof * logf(a.m.base_scale);
-          a.out_logs[b * 3 + 0] = lpb + delta;
-          a.out_logs[b * 3 + 1] = lpb;
+          a.out_logs[b * 3 + 0] = lpb_end + delta;
+          a.out_logs[b * 3 + 1] = lpb_end;
           a.out_logs[b * 3 + 2] = delta;
         }
       }
     }
     __syncthreads();
   }
+}
+
+template <int U, int H, bool DIV>
+__global__ void __launch_bounds__(NTHREADS, 1) ecnf_solve_kernel(const __grid_constant__ KernelArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ long long s_traj;
+  __shared__ float s_ctl[8];
+  Engine<U, H, DIV> eng(a.m, smem, a.scratch + (size_t)blockIdx.x * a.scratch_stride);
+  solve_body<Engine<U, H, DIV>, DIV>(a, eng, s_traj, s_ctl);
 }
 
 template <int U, int H, bool DIV>

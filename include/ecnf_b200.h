@@ -70,6 +70,10 @@ int ecnf_model_param_layout(const ecnf_model* m, int idx, char* name, int name_c
 #define ECNF_MODE_LOGPROB 4     /* get_log_prob              (sample_and_log_prob.py:41-94)   */
 
 int64_t ecnf_solve_workspace_bytes(const ecnf_model* m, int mode, int64_t B);
+/* Engine selection for the solve / vector-field entry points: 0 = automatic (tcgen05 tensor-core engine where the
+ * shape is eligible: mlp_units 128, n_hidden 64, exact divergence; fp32 SIMT otherwise), 1 = always fp32 SIMT
+ * (the accuracy reference).  Process-wide.                                                                  */
+int ecnf_set_engine(int engine);
 
 int ecnf_vf_forward(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, int64_t B,
                     float* out_f, void* ws, int64_t ws_bytes, void* stream);

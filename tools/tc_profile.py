@@ -1,0 +1,33 @@
+"""Coarse per-phase cycle breakdown of the tensor-core solve kernel (CTA 0), read back from the workspace header.
+Usage (on a GPU box): python tools/tc_profile.py [batch]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from ecnf_b200 import lib as L
+from ecnf_b200.cnf import build_cnf
+from ecnf_b200.engine import PackedParams
+from ecnf_b200.nets.egnn import init_flat_params
+
+NAMES = ["node_pre", "node_post", "meta", "build", "wait_mma", "epilogue", "messages", "sync+issue", "coords", "edge_init", "misc",
+         "  epi_ld", "  epi_act", "  epi_st", "  msg_dot", "  msg_stage", "  msg_loop", "  msg_seg", "  msg_flush", "  build_gather", "  build_act"]
+NTOP = 11
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
+cnf = build_cnf(13, 3, 0.01, 1.0, 3, (128, 128, 128), 64, 8, 1)
+eng = cnf.engine
+params = PackedParams(torch.from_numpy(init_flat_params(eng, 0, 1.0)).cuda())
+x0 = eng.base_sample(2, B)
+for it in range(2):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    x1, logs, stats = eng.solve(params, L.MODE_SAMPLE_LOGQ, x0, None, L.make_ctrl(use_fixed_step_size=True))
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+ws = eng._ws["solve"]
+prof = ws[64:64 + 8 * len(NAMES)].view(torch.int64).cpu().numpy()
+evals = int(stats[:, 2].sum()) / min(B, 148)
+tot = prof[:NTOP].sum()
+print(f"B={B} kernel {ms:.1f} ms; CTA0 ran ~{evals:.0f} evals; instrumented cycles {tot/1e6:.1f} M ({tot/evals/1e3:.0f} k/eval)")
+for nm, v in zip(NAMES, prof):
+    print(f"  {nm:12s} {v/1e6:10.2f} Mcyc  {100*v/tot:5.1f}%   {v/evals/1e3:8.1f} kcyc/eval")
