@@ -206,6 +206,7 @@ template <int U, int H, bool DIV>
 struct Engine {
   using G_ = Geo<U, H>;
   static constexpr int TR = G_::TR, LD = G_::LD, RT = G_::RT;
+  static constexpr int NT = NTHREADS;
   const EcnfModelDev& m;
   const int n, dim, D, ND, E;
   const int tid;
@@ -657,12 +658,12 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
     bool at_dtmin = false;
     const float* ein;
     if (vf_mode) {
-      for (int i = tid; i < D; i += NTHREADS) ys[i] = xin[i];
+      for (int i = tid; i < D; i += Eng::NT) ys[i] = xin[i];
       phase = PH_VF;
       t_eval = a.t_in[b];
       ein = ys;
     } else {
-      for (int i = tid; i < S; i += NTHREADS) y[i] = (i < D) ? xin[i] : 0.f;
+      for (int i = tid; i < S; i += Eng::NT) y[i] = (i < D) ? xin[i] : 0.f;
       phase = PH_F0;
       t_eval = dir * T0;
       ein = y;
@@ -676,32 +677,32 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
       ++n_evals;
       bool begin_step = false;
       if (phase == PH_VF) {
-        for (int i = tid; i < D; i += NTHREADS) a.out_x[b * D + i] = fo[i];
+        for (int i = tid; i < D; i += Eng::NT) a.out_x[b * D + i] = fo[i];
         if (DIV && tid == 0) a.out_logs[b] = fo[D];
         running = false;
       } else if (phase == PH_F0) {
         // F(tau, y) = dir * f(dir * tau, y); FSAL initialisation
-        for (int i = tid; i < S; i += NTHREADS) f0[i] = dir * fo[i];
+        for (int i = tid; i < S; i += Eng::NT) f0[i] = dir * fo[i];
         __syncthreads();
         if (c.fixed) {
           tnext = clip_to_end(tprev, tprev + fabsf(c.step_size), T1, true);
           begin_step = true;
         } else {
           // Hairer-Wanner initial step (diffrax _select_initial_step)
-          for (int i = tid; i < S; i += NTHREADS) red[i] = y[i] / (c.atol + fabsf(y[i]) * c.rtol);
+          for (int i = tid; i < S; i += Eng::NT) red[i] = y[i] / (c.atol + fabsf(y[i]) * c.rtol);
           const float d0 = rms_of_red();
-          for (int i = tid; i < S; i += NTHREADS) red[i] = f0[i] / (c.atol + fabsf(y[i]) * c.rtol);
+          for (int i = tid; i < S; i += Eng::NT) red[i] = f0[i] / (c.atol + fabsf(y[i]) * c.rtol);
           d1 = rms_of_red();
           const bool cond = (d0 < 1e-5f) || (d1 < 1e-5f);
           h0 = cond ? 1e-6f : 0.01f * d0 / d1;
-          for (int i = tid; i < S; i += NTHREADS) ys[i] = y[i] + h0 * f0[i];
+          for (int i = tid; i < S; i += Eng::NT) ys[i] = y[i] + h0 * f0[i];
           __syncthreads();
           t_eval = dir * (tprev + h0);
           ein = ys;
           phase = PH_F1;
         }
       } else if (phase == PH_F1) {
-        for (int i = tid; i < S; i += NTHREADS) red[i] = (dir * fo[i] - f0[i]) / (c.atol + fabsf(y[i]) * c.rtol);
+        for (int i = tid; i < S; i += Eng::NT) red[i] = (dir * fo[i] - f0[i]) / (c.atol + fabsf(y[i]) * c.rtol);
         const float d2 = rms_of_red() / h0;
         const float md = fmaxf(d1, d2);
         const float h1 = (md <= 1e-15f) ? fmaxf(1e-6f, h0 * 1e-3f) : powf(0.01f / md, 1.f / c.error_order);
@@ -709,7 +710,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
         tnext = clip_to_end(tprev, tprev + dt0, T1, true);
         begin_step = true;
       } else {  // PH_STAGE: stage `stage` (1..6) of the current step has just been evaluated at ys
-        for (int i = tid; i < S; i += NTHREADS) kk[stage * S + i] = (dir * fo[i]) * dt;
+        for (int i = tid; i < S; i += Eng::NT) kk[stage * S + i] = (dir * fo[i]) * dt;
         __syncthreads();
         if (stage < 6) {
           ++stage;
@@ -721,7 +722,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
             new_prev = tnext;
             new_next = tnext + dt;
           } else {
-            for (int i = tid; i < S; i += NTHREADS) {
+            for (int i = tid; i < S; i += Eng::NT) {
               float e = 0.f;
               for (int j = 0; j < 7; ++j) {
                 const float bj = c_BERR[j];
@@ -744,7 +745,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
           new_prev = fminf(new_prev, T1);
           new_next = clip_to_end(new_prev, new_next, T1, keep);
           if (keep) {
-            for (int i = tid; i < S; i += NTHREADS) { y[i] = ys[i]; f0[i] = dir * fo[i]; }
+            for (int i = tid; i < S; i += Eng::NT) { y[i] = ys[i]; f0[i] = dir * fo[i]; }
             ++n_acc;
           }
           __syncthreads();
@@ -758,7 +759,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
       }
       if (begin_step) {
         dt = tnext - tprev;
-        for (int i = tid; i < S; i += NTHREADS) kk[i] = f0[i] * dt;
+        for (int i = tid; i < S; i += Eng::NT) kk[i] = f0[i] * dt;
         __syncthreads();
         stage = 1;
         phase = PH_STAGE;
@@ -766,7 +767,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
       }
       if (running && phase == PH_STAGE) {
         // stage input: ys = y + sum_j a[stage][j] k_j ; time tprev + c[stage] dt
-        for (int i = tid; i < S; i += NTHREADS) {
+        for (int i = tid; i < S; i += Eng::NT) {
           float v = y[i];
           for (int j = 0; j < stage; ++j) {
             const float aj = c_A[stage][j];
@@ -781,7 +782,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
     }
     if (vf_mode) { __syncthreads(); continue; }
 
-    for (int i = tid; i < D; i += NTHREADS) a.out_x[b * D + i] = y[i];
+    for (int i = tid; i < D; i += Eng::NT) a.out_x[b * D + i] = y[i];
     float lpb_end = 0.f;
     if (DIV && reverse) lpb_end = base_logp(y);
     if (tid == 0) {
