@@ -110,6 +110,7 @@ extern __shared__ __align__(128) unsigned char smem_tc[];
 
 struct EngineTC {
   static constexpr int U = TCU, H = TCH;
+  static constexpr int NT = NTHREADS;
   const KernelArgs& a;     // the __grid_constant__ kernel parameter
   const EcnfModelDev& m;
   const TcImages& img;
