@@ -4,10 +4,10 @@
 
 namespace ecnf_solve_detail {
 
-// per-CTA global scratch (floats): h (current), h_in, P_s, P_r, aggregated messages
+// per-CTA global scratch (floats): h (current), h_in, P_s, P_r, aggregated messages, P_h (tensor-core engine only)
 __host__ __device__ inline int64_t scratch_floats(int n, int dim, int H, int U, bool div) {
   const int64_t ND = div ? 1 + n * dim : 1;
-  return n * ND * (2 * (int64_t)H + 3 * (int64_t)U);
+  return n * ND * (2 * (int64_t)H + 4 * (int64_t)U);
 }
 
 // byte offsets of the bf16 (hi, lo) weight images used by the tensor-core engine (ecnf_solve_tc.cuh)
@@ -21,8 +21,18 @@ struct TcImages {
 
 // shared-memory carve-up of the tensor-core engine (byte offsets), computed on the host
 struct TcSmemLayout {
-  int Wb0, Wb1, stage, G, macc, vecs, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, rowsd, rowslot, rowgrp, rdot, gi, gj,
-      giz, gv, gs1, glen, ginv, ge, bars, prof, total_bytes;
+  int bop, macc, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, colw, coloffS, coloffR, colsd, colmrow, pm, grpw, hdr,
+      pdot, wA, wB, cdbuf, egv, eglen, eginv, egs1, egiz, bars, prof, total_bytes;
+  int mrows;   // rows of the message accumulator (a window of whole receivers)
+};
+
+// tile tables of the tensor-core engine: which (group, slot) row sits in which accumulator column (ecnf_solve_tc.cuh)
+enum { TT_NODE1 = 0, TT_NODE, TT_FIRST, TT_MID, TT_LAST, TT_COUNT };
+constexpr int TC_TILE_WORDS = 208;   // 128 column words + 64 group words + 16 header words
+struct TcTabs {
+  const uint32_t* base;
+  int off[TT_COUNT];   // first tile of each kind
+  int cnt[TT_COUNT];   // tiles per kind
 };
 
 struct KernelArgs {
@@ -41,6 +51,7 @@ struct KernelArgs {
   unsigned int* counter;
   TcImages img;
   TcSmemLayout lay;
+  TcTabs tabs;
 };
 
 template <int U, int H, bool DIV>

@@ -7,8 +7,8 @@ bool tc_eligible(const ecnf_model* mdl, bool div) {
   const ecnf_config& c = mdl->cfg;
   if (!div || c.mlp_units != TCU || c.n_hidden != TCH || c.n_layers < 2) return false;
   const int D = c.n_frames * c.dim;
-  if (1 + D > 128) return false;
-  return make_tc_layout(c.n_frames, c.dim, c.n_layers).total_bytes + 1024 <= 227 * 1024;
+  if (1 + D > 127) return false;   // a (node, slot) group must fit one tile: 64 + 1 + 63 columns
+  return make_tc_layout(c.n_frames, c.dim).total_bytes + 1024 <= 227 * 1024;
 }
 
 namespace {
@@ -22,7 +22,7 @@ int64_t walk_images(const ecnf_model* mdl, TcImages* img, TcPrepList* list) {
     const int64_t o = off;
     if (list && cnt < 64) list->item[cnt] = TcPrepItem{(int)src_off, (int)o, K, N};
     ++cnt;
-    off += (int64_t)2 * K * N * 2;
+    off += (int64_t)K * 512;   // hi | lo, 128 lanes x K/2 words each
     return (int)o;
   };
   for (int b = 0; b < c.n_blocks; ++b) {
@@ -44,7 +44,21 @@ int64_t walk_images(const ecnf_model* mdl, TcImages* img, TcPrepList* list) {
 }
 }  // namespace
 
-int64_t tc_image_bytes(const ecnf_model* mdl) { return (walk_images(mdl, nullptr, nullptr) + 255) & ~255LL; }
+// tile counts / offsets of the five table kinds
+TcTabs make_tabs(const ecnf_model* mdl) {
+  TcTabs t{};
+  int off = 0;
+  for (int k = 0; k < TT_COUNT; ++k) {
+    t.off[k] = off;
+    t.cnt[k] = tc_pack(k, mdl->cfg.n_frames, mdl->cfg.dim, nullptr);
+    off += t.cnt[k];
+  }
+  return t;
+}
+int64_t tables_bytes(const TcTabs& t) { return (int64_t)(t.off[TT_COUNT - 1] + t.cnt[TT_COUNT - 1]) * TC_TILE_WORDS * 4; }
+int64_t images_bytes(const ecnf_model* mdl) { return (walk_images(mdl, nullptr, nullptr) + 255) & ~255LL; }
+
+int64_t tc_image_bytes(const ecnf_model* mdl) { return images_bytes(mdl) + ((tables_bytes(make_tabs(mdl)) + 255) & ~255LL); }
 
 int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cudaStream_t st) {
   static TcPrepList list;   // filled per call below (host-side scratch; the call is not re-entrant across threads)
@@ -59,11 +73,16 @@ int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cu
   dim3 pgrid(16, local.count);
   tc_prep_kernel<<<pgrid, 256, 0, st>>>(mdl->d_params, reinterpret_cast<unsigned char*>(image_ws), local);
   ECNF_CHECK_CUDA(cudaGetLastError());
-  const TcSmemLayout L = make_tc_layout(mdl->cfg.n_frames, mdl->cfg.dim, mdl->cfg.n_layers);
+  a.tabs = make_tabs(mdl);
+  uint32_t* tab_ws = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(image_ws) + images_bytes(mdl));
+  a.tabs.base = tab_ws;
+  tc_tables_kernel<<<1, 32, 0, st>>>(tab_ws, mdl->cfg.n_frames, mdl->cfg.dim, a.tabs);
+  ECNF_CHECK_CUDA(cudaGetLastError());
+  const TcSmemLayout L = make_tc_layout(mdl->cfg.n_frames, mdl->cfg.dim);
   a.lay = L;
   const size_t smem = (size_t)L.total_bytes;
   ECNF_CHECK_CUDA(cudaFuncSetAttribute(ecnf_solve_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ecnf_solve_tc_kernel<<<grid, NTHREADS, smem, st>>>(a);
+  ecnf_solve_tc_kernel<<<grid, TC_NT, smem, st>>>(a);
   ECNF_CHECK_CUDA(cudaGetLastError());
   return ECNF_OK;
 }

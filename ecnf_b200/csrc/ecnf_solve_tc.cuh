@@ -1,19 +1,29 @@
 // Engine A on the 5th-generation tensor cores (tcgen05 + TMEM), for mlp_units = 128, n_invariant_feat_hidden = 64
 // (DW4 / LJ13 shapes) with the exact divergence.
 //
-// Same algorithm, tile structure and tangent-row scheme as the fp32 SIMT engine (ecnf_solve_impl.cuh); what changes
-// is where the rows live and who multiplies:
-//   * a row tile is 128 rows = the 128 lanes of tensor memory; thread t owns row (t & 127) and the 64 columns
-//     [64*(t>>7), +64) of it -- the natural tcgen05.ld/st 32x32b ownership, so no shuffles anywhere;
-//   * activations never touch shared memory between layers: accumulator (TMEM, fp32) -> registers -> bias/SiLU or the
-//     tangent rule -> split into bf16 (hi, lo) -> A operand written back to TMEM with tcgen05.st (2 bf16 per column);
-//   * every Dense layer is 3 x (K/16) tcgen05.mma (A from TMEM, B from shared memory): hi*hi + lo*hi + hi*lo with
-//     fp32 accumulation, i.e. ~2^-16 relative error per product (measured 4e-6 by tools/probe_tc.cu) -- single-pass
-//     bf16/tf32 misses the 1e-4 tolerance on log q;
-//   * weights are pre-split into bf16 (hi, lo) images in the MMA's canonical no-swizzle K-major layout by a prep kernel
-//     and streamed from L2 with cp.async.bulk into two 64 KB buffers, one layer ahead;
-//   * two row tiles are in flight (TMEM holds 2 x (128 accumulator + 128 operand columns)): while the 256 threads run
-//     the epilogue of one tile, the tensor core multiplies the other.
+// Same algorithm and tangent-row scheme as the fp32 SIMT engine (ecnf_solve_impl.cuh); the formulation is transposed
+// ("feature on lane") so that everything the tangent rule needs is thread-local:
+//
+//     D^T[out feature (TMEM lane), row (TMEM column)] = W^T (A operand, TMEM) x Act^T (B operand, shared memory)
+//
+//   * a row tile is up to 128 rows = 128 accumulator COLUMNS; thread (f, hh) of the 256 epilogue threads owns output
+//     feature f = lane f and the 64 columns [64 hh, +64) -- the natural tcgen05.ld 32x32b ownership;
+//   * rows are (edge or node, slot) with slot 0 the primal value and slot 1+k the tangent in input direction k.  A tile
+//     is two half-blocks of 64 columns made of segments "primal column, then its tangent columns" (a group split over
+//     the two halves repeats its primal column), so the activation rule  a = silu(z + b) / a-dot = silu'(z) z-dot
+//     is a running scalar per thread: no shared-memory exchange and no barrier between the layers of the MLP chain;
+//   * activations: accumulator (TMEM, fp32) -> registers -> rule -> bf16 (hi, lo) split -> B operand in shared memory,
+//     MN-major no-swizzle canonical layout (8 rows of one feature = one 16-byte store, a warp stores 512 contiguous B);
+//   * weights: pre-split bf16 (hi, lo) images, loaded from L2 straight into TENSOR MEMORY (tcgen05.st) by the epilogue
+//     threads, double buffered, so the MMA reads only B from shared memory;
+//   * every Dense layer is 3 x (K/16) tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-17 relative per
+//     product, measured 4e-6 by tools/probe_tc2.cu) -- single-pass bf16/tf32 misses the 1e-4 tolerance on log q;
+//   * two tiles are in flight (two accumulators, two B buffers): while the epilogue threads work on one, the tensor
+//     core multiplies the other.  A dedicated warp issues the MMAs; hand-over is by mbarriers only
+//     (epilogue -> "ready[s]" -> MMA -> tcgen05.commit -> "done[s]" -> epilogue);
+//   * the only cross-lane work are the two Dense(1) heads (attention logit, coordinate head): a 62-shuffle transposing
+//     butterfly per warp + one 4-way sum through shared memory;
+//   * tile composition (which (group, slot) sits in which column) is precomputed per (n, dim, kind) into a table.
 #pragma once
 #include "ecnf_solve_impl.cuh"
 #include "ecnf_tc.cuh"
@@ -23,21 +33,111 @@ namespace ecnf_solve_detail {
 using namespace ecnf_tc;
 
 constexpr int TCU = 128, TCH = 64;
-constexpr int TC_GMAX = 32;        // groups (edges / nodes) per tile
-constexpr int TC_WBYTES = 65536;   // one weight buffer: hi + lo image of a 128 x 128 layer
-constexpr int TC_SLD = 65;          // staging row stride (floats): odd, so lanes = rows is conflict-free
+constexpr int TC_NT = 288;          // 8 epilogue warps + 1 MMA-issue warp
+constexpr int TC_EPI = 256;
+constexpr int TC_BOP = 65536;       // one B-operand buffer: hi image [K = 128][N = 128] + lo image
+constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;
+constexpr int TC_WCOL = 256;        // first TMEM column of the weight buffers (accumulators: [0, 128) and [128, 256))
 
-__host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim, int n_layers) {
-  const int D = n * dim, S = D + 1;
+// column word of a tile table
+constexpr uint32_t CW_VALID = 1u << 31, CW_PRIMAL = 1u << 30, CW_DUP = 1u << 29;
+__host__ __device__ __forceinline__ int cw_gid(uint32_t w) { return (int)(w & 1023u); }
+__host__ __device__ __forceinline__ int cw_q(uint32_t w) { return (int)((w >> 10) & 255u); }
+__host__ __device__ __forceinline__ int cw_pc(uint32_t w) { return (int)((w >> 18) & 63u); }
+enum { TH_NC0 = 0, TH_NC1, TH_N, TH_G0, TH_NG, TH_WIN, TH_FLUSH, TH_IFIRST, TH_ILAST };
+
+__host__ __device__ inline int tc_macc_rows(int n, int dim) {
+  const int ND = 1 + n * dim;
+  const int rw = 40 / ND > 1 ? 40 / ND : 1;
+  return (rw < n ? rw : n) * ND;
+}
+
+// Packs the groups (nodes or edges) of one table kind into tiles; returns the tile count, writes them when out != null.
+// Tile = 128 column words | 64 group words (slot split + first columns of the group's segments) | 16 header words.
+__host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) {
+  const int D = n * dim, ND = 1 + D;
+  const bool edge = kind >= TT_FIRST;
+  const int ngroups = edge ? n * (n - 1) : n;
+  const int r = kind == TT_NODE1 ? 1 : kind == TT_NODE ? ND : kind == TT_FIRST ? 1 + 2 * dim : kind == TT_MID ? ND : 1 + dim;
+  // message-accumulator window: tiles of the message-passing kinds never span two windows of receivers
+  const int window = (kind == TT_FIRST || kind == TT_MID) ? (tc_macc_rows(n, dim) / ND) * (n - 1) : 0;
+  int tile = 0, used0 = 0, used1 = 0, half = 0, ng = 0, g0 = 0;
+  auto tp = [&](int t) { return out + (size_t)t * TC_TILE_WORDS; };
+  auto close = [&](int gnext, int flush) {
+    if (ng == 0) return;
+    if (out) {
+      uint32_t* h = tp(tile) + 192;
+      const int n1 = (used1 + 15) & ~15, n0 = (used0 + 15) & ~15;
+      h[TH_NC0] = (uint32_t)used0;
+      h[TH_NC1] = (uint32_t)used1;
+      h[TH_N] = (uint32_t)(used1 > 0 ? 64 + n1 : (n0 > 16 ? n0 : 16));
+      h[TH_G0] = (uint32_t)g0;
+      h[TH_NG] = (uint32_t)ng;
+      const int wstart = window ? (g0 / window) * window : 0;
+      h[TH_WIN] = (uint32_t)(edge ? wstart / (n - 1) : 0);
+      h[TH_FLUSH] = (uint32_t)flush;
+      h[TH_IFIRST] = (uint32_t)(edge ? g0 / (n - 1) : g0);
+      h[TH_ILAST] = (uint32_t)(edge ? (g0 + ng - 1) / (n - 1) : g0 + ng - 1);
+    }
+    ++tile;
+    used0 = used1 = 0; half = 0; ng = 0; g0 = gnext;
+  };
+  // one segment: [repeated primal] + slots q0..q1-1 from column col0 on
+  auto seg = [&](int g, int col0, int q0, int q1, bool dup) {
+    if (!out) return;
+    uint32_t* cw = tp(tile);
+    int c = col0;
+    const uint32_t common = CW_VALID | (uint32_t)g | ((uint32_t)(col0 & 63) << 18);
+    if (dup) cw[c++] = common | CW_PRIMAL | CW_DUP;
+    for (int q = q0; q < q1; ++q) cw[c++] = common | (q == 0 ? CW_PRIMAL : 0u) | ((uint32_t)q << 10);
+  };
+  for (int g = 0; g < ngroups; ++g) {
+    if (window && g > 0 && g % window == 0) close(g, 1);
+    for (;;) {
+      if (ng == 0 && used0 == 0 && out)
+        for (int k = 0; k < TC_TILE_WORDS; ++k) tp(tile)[k] = 0;
+      if (half == 0) {
+        const int rem = 64 - used0;
+        if (r <= rem) {
+          seg(g, used0, 0, r, false);
+          if (out) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)used0 << 8);
+          used0 += r;
+          break;
+        }
+        if (rem >= 2 && 1 + r - rem <= 64) {
+          seg(g, used0, 0, rem, false);
+          seg(g, 64, rem, r, true);
+          if (out) tp(tile)[128 + ng] = (uint32_t)rem | ((uint32_t)used0 << 8) | (64u << 16);
+          used0 = 64; used1 = 1 + r - rem; half = 1;
+          break;
+        }
+        half = 1;
+        if (r > 64) { close(g, 0); }
+        continue;
+      }
+      const int rem = 64 - used1;
+      if (r <= rem) {
+        seg(g, 64 + used1, 0, r, false);
+        if (out) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)(64 + used1) << 8);
+        used1 += r;
+        break;
+      }
+      close(g, 0);
+    }
+    ++ng;
+  }
+  close(ngroups, window ? 1 : 0);
+  return tile;
+}
+
+__host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim) {
+  const int D = n * dim, S = D + 1, E = n * (n - 1);
   TcSmemLayout L;
   int o = 0;
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
-  L.Wb0 = take(TC_WBYTES);
-  L.Wb1 = take(TC_WBYTES);
-  L.stage = take(128 * TC_SLD * 4);        // staging [128 rows][65]; also the primal-activation hand-over buffer
-  L.G = take(TC_GMAX * TCU * 4);
-  L.macc = take((1 + D) * TCU * 4);       // aggregated messages of the receiver being processed
-  L.vecs = take((2 * n_layers - 1 + 3) * TCU * 4);       // per-block vectors: layer biases, w_d, attention / head weights
+  L.bop = take(2 * TC_BOP);
+  L.mrows = tc_macc_rows(n, dim);
+  L.macc = take(2 * L.mrows * TCU * 4);    // aggregated messages of the receiver window, one copy per column half
   L.xt = take(D * D * 4);
   L.xtacc = take(D * D * 4);
   L.dacc = take(D * 4);
@@ -49,86 +149,58 @@ __host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim, int n_lay
   L.cvec = take(64 * 4);
   L.ode = take(11 * S * 4);
   L.red = take((S + 16) * 4);
-  L.rowsd = take(2 * 128 * 4);
-  L.rowslot = take(2 * 128 * 4);
-  L.rowgrp = take(2 * 128 * 4);
-  L.rdot = take(2 * 2 * 128 * 4);
-  L.gi = take(2 * TC_GMAX * 4);
-  L.gj = take(2 * TC_GMAX * 4);
-  L.giz = take(2 * TC_GMAX * 4);
-  L.gv = take(2 * TC_GMAX * 3 * 4);
-  L.gs1 = take(2 * TC_GMAX * 4);
-  L.glen = take(2 * TC_GMAX * 4);
-  L.ginv = take(2 * TC_GMAX * 4);
-  L.ge = take(2 * TC_GMAX * 4);
+  L.colw = take(2 * 128 * 4);
+  L.coloffS = take(2 * 128 * 4);
+  L.coloffR = take(2 * 128 * 4);
+  L.colsd = take(2 * 128 * 4);
+  L.colmrow = take(2 * 128 * 4);
+  L.pm = take(2 * 4 * 4);
+  L.grpw = take(2 * 64 * 4);
+  L.hdr = take(2 * 16 * 4);
+  L.pdot = take(2 * 8 * 64 * 4);
+  L.wA = take(8 * 64 * 4);
+  L.wB = take(8 * 64 * 4);
+  L.cdbuf = take(2 * 128 * 3 * 4);
+  L.egv = take(E * 3 * 4);
+  L.eglen = take(E * 4);
+  L.eginv = take(E * 4);
+  L.egs1 = take(E * 4);
+  L.egiz = take(E * 4);
   L.bars = take(64);
   L.prof = take(32 * 8);
   L.total_bytes = o;
   return L;
 }
 
-extern __shared__ __align__(128) unsigned char smem_tc[];
+extern __shared__ __align__(1024) unsigned char smem_tc[];
 
 // Every buffer is addressed as (shared-memory base + offset from the kernel parameters): the offsets are constant-bank
 // loads, so no pointer has to be kept alive in (or spilled from) registers across the very large inlined body.
 #define TCF(field) (reinterpret_cast<float*>(smem_tc + a.lay.field))
 #define TCI(field) (reinterpret_cast<int*>(smem_tc + a.lay.field))
-#define stage TCF(stage)
-#define G TCF(G)
-#define macc TCF(macc)
-#define vecs TCF(vecs)
-#define xt TCF(xt)
-#define xtacc TCF(xtacc)
-#define dacc TCF(dacc)
-#define xs TCF(xs)
-#define xs0 TCF(xs0)
-#define xacc TCF(xacc)
-#define mu TCF(mu)
-#define tau TCF(tau)
-#define cvec TCF(cvec)
-#define rowsd TCF(rowsd)
-#define rdot TCF(rdot)
-#define gv TCF(gv)
-#define gs1 TCF(gs1)
-#define glen TCF(glen)
-#define ginv TCF(ginv)
-#define ge TCF(ge)
-#define rowslot TCI(rowslot)
-#define rowgrp TCI(rowgrp)
-#define gi TCI(gi)
-#define gj TCI(gj)
-#define giz TCI(giz)
-#define mbar_mma (reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars))
-#define mbar_w (reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + 2)
-#define tmem_slot (reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars + 32))
-#define prof_s (reinterpret_cast<long long*>(smem_tc + a.lay.prof))
-#define hA (a.scratch + (size_t)blockIdx.x * a.scratch_stride)
-#define hB (hA + (size_t)n * ND * H)
-#define Ps (hB + (size_t)n * ND * H)
-#define Pr (Ps + (size_t)n * ND * U)
-#define Mg (Pr + (size_t)n * ND * U)
+#define TCW(field) (reinterpret_cast<uint32_t*>(smem_tc + a.lay.field))
 
 struct EngineTC {
   static constexpr int U = TCU, H = TCH;
-  static constexpr int NT = NTHREADS;
+  static constexpr int NT = TC_NT;
   const KernelArgs& a;     // the __grid_constant__ kernel parameter
   const EcnfModelDev& m;
   const TcImages& img;
   const int n, dim, D, ND, E;
-  const int tid, row, ch, warp;
+  const int tid, f, hh, warp, lane;
+  const bool is_epi;
   uint32_t tmem;         // TMEM base address
   uint32_t lane_addr;    // (32 * (warp & 3)) << 16
-  uint32_t ph_mma0, ph_mma1;   // completed-phase counters of the two MMA barriers
-  uint32_t wq_head;      // weight loads issued so far (monotonic; buffer = seq & 1, parity = (seq >> 1) & 1)
-  // coarse cycle counters (compile with -DECNF_TC_PROFILE; CTA 0 dumps them into the workspace header, tools/tc_profile.py)
-  enum { P_NODE_PRE, P_NODE_POST, P_META, P_BUILD, P_WAIT_MMA, P_EPI, P_MSG, P_SYNC_ISSUE, P_COORDS, P_EDGE_INIT, P_EVAL_MISC,
-         P_EPI_LD, P_EPI_ACT, P_EPI_ST, P_MSG_DOT, P_MSG_STAGE, P_MSG_LOOP, P_MSG_SEG, P_MSG_FLUSH, P_BUILD_GATHER, P_BUILD_ACT, P_NCOUNT };
+  uint32_t ph0, ph1;     // phase counters of the two slots (ready[] for the issue warp, done[] for the epilogue threads)
+
+  enum { P_NODE_PRE, P_EDGE, P_NODE_POST, P_WAIT, P_BUILD, P_EPI, P_MSG, P_COORD, P_WLOAD, P_META, P_CTRL_WAIT, P_MISC, P_NCOUNT };
 #ifdef ECNF_TC_PROFILE
   long long prof_t0, prof_t1;
+  __device__ __forceinline__ long long* prof_s() const { return reinterpret_cast<long long*>(smem_tc + a.lay.prof); }
   __device__ __forceinline__ void pbeg() { prof_t0 = clock64(); }
-  __device__ __forceinline__ void pend(int k) { const long long t1 = clock64(); if (tid == 0) prof_s[k] += t1 - prof_t0; prof_t0 = t1; }
+  __device__ __forceinline__ void pend(int k) { const long long t1 = clock64(); if (tid == 0) prof_s()[k] += t1 - prof_t0; prof_t0 = t1; }
   __device__ __forceinline__ void qbeg() { prof_t1 = clock64(); }
-  __device__ __forceinline__ void qend(int k) { const long long t1 = clock64(); if (tid == 0) prof_s[k] += t1 - prof_t1; prof_t1 = t1; }
+  __device__ __forceinline__ void qend(int k) { const long long t1 = clock64(); if (tid == 0 || tid == TC_EPI) prof_s()[k] += t1 - prof_t1; prof_t1 = t1; }
 #else
   __device__ __forceinline__ void pbeg() {}
   __device__ __forceinline__ void pend(int) {}
@@ -138,694 +210,767 @@ struct EngineTC {
 
   __device__ __forceinline__ float* ode_ptr() const { return TCF(ode); }
   __device__ __forceinline__ float* red_ptr() const { return TCF(red); }
+  __device__ __forceinline__ uint64_t* bar_ready(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + s; }
+  __device__ __forceinline__ uint64_t* bar_done(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + 2 + s; }
+  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars + 32); }
+  // per-CTA global scratch (L2 resident): h, h_in [n][ND][H]; P_s, P_r, P_h, aggregated messages [n][ND][U]
+  __device__ __forceinline__ float* hA() const { return a.scratch + (size_t)blockIdx.x * a.scratch_stride; }
+  __device__ __forceinline__ float* hB() const { return hA() + (size_t)n * ND * H; }
+  __device__ __forceinline__ float* Ps() const { return hB() + (size_t)n * ND * H; }
+  __device__ __forceinline__ float* Pr() const { return Ps() + (size_t)n * ND * U; }
+  __device__ __forceinline__ float* Mg() const { return Pr() + (size_t)n * ND * U; }
+  __device__ __forceinline__ float* Ph() const { return Mg() + (size_t)n * ND * U; }
 
   __device__ __forceinline__ EngineTC(const KernelArgs& a_)
       : a(a_), m(a_.m), img(a_.img), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim), ND(1 + a_.m.n * a_.m.dim),
-        E(a_.m.n * (a_.m.n - 1)), tid(threadIdx.x), row(threadIdx.x & 127), ch(threadIdx.x >> 7), warp(threadIdx.x >> 5) {
+        E(a_.m.n * (a_.m.n - 1)), tid(threadIdx.x), f(threadIdx.x & 127), hh((threadIdx.x >> 7) & 1), warp(threadIdx.x >> 5),
+        lane(threadIdx.x & 31), is_epi(threadIdx.x < TC_EPI) {
     if (tid == 0) {
-      mbar_init(&mbar_mma[0], 1); mbar_init(&mbar_mma[1], 1);
-      mbar_init(&mbar_w[0], 1); mbar_init(&mbar_w[1], 1);
-      for (int k = 0; k < P_NCOUNT; ++k) prof_s[k] = 0;
+      mbar_init(bar_ready(0), TC_EPI); mbar_init(bar_ready(1), TC_EPI);
+      mbar_init(bar_done(0), 1); mbar_init(bar_done(1), 1);
+#ifdef ECNF_TC_PROFILE
+      for (int k = 0; k < P_NCOUNT; ++k) prof_s()[k] = 0;
+#endif
     }
     __syncwarp();
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc(tmem_slot(), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    tmem = *tmem_slot;
+    tmem = *tmem_slot();
     lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    ph_mma0 = ph_mma1 = 0;
-    wq_head = 0;
+    ph0 = ph1 = 0;
+    if (is_epi) {   // accumulators start finite (columns beyond a tile's N are read but never used)
+      uint32_t z[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) z[c] = 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmem_st32(tmem + lane_addr + 128u * hh + 32u * q, z);
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
   }
   __device__ __forceinline__ void finish(long long* out) {
+#ifdef ECNF_TC_PROFILE
     if (out && tid == 0 && blockIdx.x == 0)
-      for (int k = 0; k < P_NCOUNT; ++k) out[k] = prof_s[k];
+      for (int k = 0; k < P_NCOUNT; ++k) out[k] = prof_s()[k];
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
   }
 
-  // ---- TMEM map: slot s -> accumulator [256 s, +128), A hi [256 s + 128, +64), A lo [256 s + 192, +64)
-  __device__ __forceinline__ uint32_t acc_of(int s) const { return tmem + 256u * s; }
-  __device__ __forceinline__ uint32_t ahi_of(int s) const { return tmem + 256u * s + 128u; }
-  __device__ __forceinline__ uint32_t alo_of(int s) const { return tmem + 256u * s + 192u; }
-
-  // ---- weight queue ------------------------------------------------------------------------------------------
-  // Issue the load of one weight image (hi + lo) into buffer (seq & 1).  The caller guarantees that every MMA that
-  // read the previous content of that buffer has completed.
-  __device__ __forceinline__ void wq_load(int img_off, int bytes) {
-    const uint32_t seq = wq_head++;
-    if (tid == 0) {
-      uint64_t* bar = &mbar_w[seq & 1];
-      mbar_expect_tx(bar, (uint32_t)bytes);
-      unsigned char* dst = smem_tc + a.lay.Wb0 + (seq & 1) * TC_WBYTES;
-      const unsigned char* src = img.base + img_off;
-      for (int o = 0; o < bytes; o += 16384) bulk_g2s(dst + o, src + o, (uint32_t)min(16384, bytes - o), bar);
-    }
-    __syncwarp();
+  // ---- hand-over between the epilogue threads and the MMA-issue warp ----------------------------------------------
+  __device__ __forceinline__ void epi_bar() const { named_bar_sync(1, TC_EPI); }
+  // epilogue: my part of slot s's next operands (B in shared memory, weights / drained accumulator in TMEM) is complete
+  __device__ __forceinline__ void arrive_ready(int s) {
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(bar_ready(s));
   }
-  // thread 0 only: block until the image of sequence number `seq` has landed; returns its shared-memory address
-  __device__ __forceinline__ uint32_t wq_wait(uint32_t seq) {
-    mbar_wait(&mbar_w[seq & 1], (seq >> 1) & 1);
-    return smem_u32(smem_tc + a.lay.Wb0) + (seq & 1) * TC_WBYTES;
+  __device__ __forceinline__ void wait_slot(uint64_t* bar0, uint64_t* bar1, int s) {
+    if (s == 0) { mbar_wait(bar0, ph0 & 1); ph0++; }
+    else { mbar_wait(bar1, ph1 & 1); ph1++; }
+    tc_fence_after();
   }
+  __device__ __forceinline__ void wait_done(int s) { qbeg(); wait_slot(bar_done(0), bar_done(1), s); qend(P_WAIT); }
+  __device__ __forceinline__ void ctrl_wait_ready(int s) { qbeg(); wait_slot(bar_ready(0), bar_ready(1), s); qend(P_CTRL_WAIT); }
 
-  // ---- MMA issue (thread 0): acc (+)= A[128 x K] (TMEM hi/lo) x W[K x N] (3-pass split) -------------------------
-  // Called by ALL lanes of warp 0 (warp-uniform operands stay in uniform registers); one elected lane issues.
-  __device__ __forceinline__ void issue_mma(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t wsm, int K, int N,
-                                            bool accumulate, uint64_t* commit_bar) {
+  // issue warp: acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s] (K x N), 3-pass split; commit -> done[s]
+  __device__ __forceinline__ void issue_mma(int s, uint32_t a_col, int K, int N) {
     __syncwarp();
-    if (!elect_one()) return;
-    const uint32_t idesc = make_idesc_bf16(128, N);
-    const uint32_t lbo = (uint32_t)(N / 8) * 128u;
-    uint64_t bh = make_sdesc(wsm, lbo, 128);
-    uint64_t bl = make_sdesc(wsm + (uint32_t)(K * N * 2), lbo, 128);
-    const uint64_t step = (uint64_t)((2u * lbo) >> 4);   // the start-address field advances by two K chunks per MMA
-    const int nk = K / 16;
-    mma_ts(acc, a_hi, bh, idesc, accumulate ? 1u : 0u);
-    mma_ts(acc, a_lo, bh, idesc, 1u);
-    mma_ts(acc, a_hi, bl, idesc, 1u);
-    for (int ks = 1; ks < nk; ++ks) {
-      bh += step; bl += step; a_hi += 8; a_lo += 8;
-      mma_ts(acc, a_hi, bh, idesc, 1u);
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_B_MN;
+      const uint32_t bsm = smem_u32(smem_tc + a.lay.bop) + (uint32_t)s * TC_BOP;
+      uint64_t bh = make_sdesc(bsm, TC_LBO, TC_SBO);
+      uint64_t bl = make_sdesc(bsm + 32768u, TC_LBO, TC_SBO);
+      const uint32_t acc = tmem + 128u * s;
+      uint32_t a_hi = tmem + a_col, a_lo = tmem + a_col + (uint32_t)(K >> 1);
+      const int nk = K >> 4;
+      mma_ts(acc, a_hi, bh, idesc, 0u);
       mma_ts(acc, a_lo, bh, idesc, 1u);
       mma_ts(acc, a_hi, bl, idesc, 1u);
+      for (int ks = 1; ks < nk; ++ks) {
+        bh += (2u * TC_LBO) >> 4; bl += (2u * TC_LBO) >> 4; a_hi += 8; a_lo += 8;
+        mma_ts(acc, a_hi, bh, idesc, 1u);
+        mma_ts(acc, a_lo, bh, idesc, 1u);
+        mma_ts(acc, a_hi, bl, idesc, 1u);
+      }
+      mma_commit(bar_done(s));
     }
-    if (commit_bar) mma_commit(commit_bar);   // same thread as the MMAs: tracks their completion
-  }
-  // all threads: make this thread's TMEM stores/loads visible, CTA barrier, then the issuer may proceed
-  __device__ __forceinline__ void tc_sync() {
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-  }
-  __device__ __forceinline__ void wait_mma(int s) {
-    if (s == 0) { mbar_wait(&mbar_mma[0], ph_mma0 & 1); ph_mma0++; }
-    else { mbar_wait(&mbar_mma[1], ph_mma1 & 1); ph_mma1++; }
-    tc_fence_after();
+    __syncwarp();
   }
 
-  // ---- per-thread row helpers ----------------------------------------------------------------------------------
-  __device__ __forceinline__ void ld_acc64(uint32_t acc, float (&v)[64]) {
-    uint32_t a[32], b[32];
-    tmem_ld32(acc + lane_addr + 64u * ch, a);
-    tmem_ld32(acc + lane_addr + 64u * ch + 32u, b);
+  // ---- per-thread column helpers (thread (f, hh): feature f, columns [64 hh, +64) of slot s) -----------------------
+  __device__ __forceinline__ void ld_acc(int s, float (&v)[64]) {
+    uint32_t x[32], y[32];
+    const uint32_t addr = tmem + 128u * s + lane_addr + 64u * hh;
+    tmem_ld32(addr, x);
+    tmem_ld32(addr + 32u, y);
     tmem_wait_ld();
 #pragma unroll
-    for (int c = 0; c < 32; ++c) { v[c] = __uint_as_float(a[c]); v[32 + c] = __uint_as_float(b[c]); }
+    for (int c = 0; c < 32; ++c) { v[c] = __uint_as_float(x[c]); v[32 + c] = __uint_as_float(y[c]); }
   }
-  // write this thread's 64 K-values [64 ch, +64) of its row as bf16 (hi, lo) into the A operand of a slot
-  __device__ __forceinline__ void st_a64(uint32_t a_hi, uint32_t a_lo, const float (&v)[64]) {
-    uint32_t h[32], l[32];
+  // B operand of slot s <- v (K row = my feature), bf16 hi / lo
+  __device__ __forceinline__ void write_B(int s, const float (&v)[64]) {
+    unsigned char* base = smem_tc + a.lay.bop + s * TC_BOP + (8 * hh) * (int)TC_SBO + f * 16;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) split_pack(v[2 * c], v[2 * c + 1], h[c], l[c]);
-    tmem_st32(a_hi + lane_addr + 32u * ch, h);
-    tmem_st32(a_lo + lane_addr + 32u * ch, l);
-  }
-  // bias + SiLU on primal rows / silu'(z_primal) * z on tangent rows.  The few primal rows of a tile hand their
-  // pre-activations over through shared memory (PA = the staging buffer) so that ALL threads share the transcendental
-  // work; G returns silu'.  Must be called by all 256 threads (CTA barriers inside).  valid = row < nrows.
-  __device__ __forceinline__ void act_rule(float (&v)[64], const float* bias, bool valid, bool primal, int grp,
-                                           int ngroups) {
-    float* PA = stage;
-    if (valid && primal) {
+    for (int g8 = 0; g8 < 8; ++g8) {
+      uint32_t h[4], l[4];
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) b = *reinterpret_cast<const float4*>(bias + 64 * ch + 4 * c4);
-        *reinterpret_cast<float4*>(PA + grp * U + 64 * ch + 4 * c4) =
-            make_float4(v[4 * c4] + b.x, v[4 * c4 + 1] + b.y, v[4 * c4 + 2] + b.z, v[4 * c4 + 3] + b.w);
-      }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < ngroups * U; idx += NTHREADS) {
-      const float z = PA[idx];
-      const float s = __fdividef(1.f, 1.f + __expf(-z));
-      PA[idx] = z * s;
-      G[idx] = s * (1.f + z * (1.f - s));
-    }
-    __syncthreads();
-    if (valid) {
-      const float* src = (primal ? PA : G) + grp * U + 64 * ch;
-#pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        const float4 g = *reinterpret_cast<const float4*>(src + 4 * c4);
-        if (primal) {
-          v[4 * c4] = g.x; v[4 * c4 + 1] = g.y; v[4 * c4 + 2] = g.z; v[4 * c4 + 3] = g.w;
-        } else {
-          v[4 * c4] *= g.x; v[4 * c4 + 1] *= g.y; v[4 * c4 + 2] *= g.z; v[4 * c4 + 3] *= g.w;
-        }
-      }
+      for (int p = 0; p < 4; ++p) split_pack(v[8 * g8 + 2 * p], v[8 * g8 + 2 * p + 1], h[p], l[p]);
+      *reinterpret_cast<uint4*>(base + g8 * (int)TC_SBO) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(base + 32768 + g8 * (int)TC_SBO) = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
-  __device__ __forceinline__ float dot64(const float (&v)[64], const float* w) const {
-    float s = 0.f;
+  // bias + SiLU on primal columns, silu'(z_primal) * z on the tangent columns that follow them
+  __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int s) {
+    const uint32_t m0 = TCW(pm)[s * 4 + 2 * hh], m1 = TCW(pm)[s * 4 + 2 * hh + 1];
+    float cur = 0.f;
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 ww = *reinterpret_cast<const float4*>(w + 64 * ch + 4 * c4);
-      s = fmaf(v[4 * c4], ww.x, s); s = fmaf(v[4 * c4 + 1], ww.y, s);
-      s = fmaf(v[4 * c4 + 2], ww.z, s); s = fmaf(v[4 * c4 + 3], ww.w, s);
-    }
-    return s;
-  }
-  __device__ __forceinline__ void load_row64(const float* src, float (&v)[64]) const {
-#pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
-      v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
-    }
-  }
-  __device__ __forceinline__ void store_row64(float* dst, const float (&v)[64]) const {
-#pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4)
-      *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-  }
-
-  // =============================================================================================================
-  // node phase 1: h_in = [h | tau] Wd + bd ; P_s = h_in We0[0:H] ; P_r = h_in We0[H:2H] + be0
-  // =============================================================================================================
-  __device__ __forceinline__ void node_pre(int b, bool htan) {
-    const EcnfBlockParams& bp = m.blk[b];
-    const TcImgBlock& ib = img.blk[b];
-    if (tid < H) {
-      float cv = bp.bd[tid];
-      for (int k = 0; k < m.T; ++k) cv = fmaf(tau[k], bp.Wd[(H + k) * H + tid], cv);
-      cvec[tid] = cv;
-    }
-    const int r = htan ? ND : 1;
-    const int gpt = min(128 / r, TC_GMAX);
-    for (int node0 = 0; node0 < n; node0 += gpt) {
-      const int nn = min(gpt, n - node0), nrows = nn * r;
-      const bool valid = row < nrows;
-      const int g = valid ? row / r : 0, q = row - g * r;
-      const bool primal = (q == 0);
-      const uint32_t s0 = wq_head;
-      wq_load(ib.Wd, 2 * H * H * 2);
-      wq_load(ib.We0s, 2 * H * U * 2);
-      float v[64];
-      // A <- h rows (K = 64: only the ch == 0 half of the threads carries data)
-      if (ch == 0) {
-        if (valid) load_row64(hA + ((size_t)(node0 + g) * ND + q) * H, v);
-        else {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] = 0.f;
-        }
-        st_a64(ahi_of(0), alo_of(0), v);
-      }
-      tc_sync();
-      if (warp == 0) { const uint32_t w = wq_wait(s0); issue_mma(acc_of(0), ahi_of(0), alo_of(0), w, H, H, false, &mbar_mma[0]); }
-      wait_mma(0);
-      wq_load(ib.We0r, 2 * H * U * 2);   // buffer of Wd is free again
-      if (ch == 0) {
-        ld_acc64(acc_of(0), v);
-        if (valid && primal) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] += cvec[c];
-        }
-        if (valid) store_row64(hB + ((size_t)(node0 + g) * ND + q) * H, v);
-        st_a64(ahi_of(0), alo_of(0), v);
-      }
-      tc_sync();
-      if (warp == 0) {
-        const uint32_t w1 = wq_wait(s0 + 1);
-        issue_mma(acc_of(0), ahi_of(0), alo_of(0), w1, H, U, false, nullptr);
-        const uint32_t w2 = wq_wait(s0 + 2);
-        issue_mma(acc_of(1), ahi_of(0), alo_of(0), w2, H, U, false, &mbar_mma[0]);
-      }
-      wait_mma(0);
-      ld_acc64(acc_of(0), v);
-      if (valid) store_row64(Ps + ((size_t)(node0 + g) * ND + q) * U + 64 * ch, v);
-      ld_acc64(acc_of(1), v);
-      if (valid) {
-        if (primal) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] += bp.be[0][64 * ch + c];
-        }
-        store_row64(Pr + ((size_t)(node0 + g) * ND + q) * U + 64 * ch, v);
-      }
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-    }
-  }
-
-  // =============================================================================================================
-  // node phase 2: h <- phi_h([M | h_in]) + h_in
-  // =============================================================================================================
-  __device__ __forceinline__ void node_post(int b, bool htan) {
-    const EcnfBlockParams& bp = m.blk[b];
-    const TcImgBlock& ib = img.blk[b];
-    const int L = m.L;
-    const int r = ND;
-    const int gpt = min(128 / r, TC_GMAX);
-    for (int node0 = 0; node0 < n; node0 += gpt) {
-      const int nn = min(gpt, n - node0), nrows = nn * r;
-      const bool valid = row < nrows;
-      const int g = valid ? row / r : 0, q = row - g * r;
-      const bool primal = (q == 0);
-      uint32_t seq = wq_head;
-      wq_load(ib.Wh0m, 2 * U * U * 2);
-      wq_load(ib.Wh0h, 2 * H * U * 2);
-      float v[64];
-      if (valid) load_row64(Mg + ((size_t)(node0 + g) * ND + q) * U + 64 * ch, v);
-      else {
-#pragma unroll
-        for (int c = 0; c < 64; ++c) v[c] = 0.f;
-      }
-      st_a64(ahi_of(0), alo_of(0), v);
-      tc_sync();
-      if (warp == 0) { const uint32_t w = wq_wait(seq); issue_mma(acc_of(0), ahi_of(0), alo_of(0), w, U, U, false, &mbar_mma[0]); }
-      wait_mma(0);
-      wq_load(L > 1 ? ib.Wh[1] : ib.WhL, L > 1 ? 2 * U * U * 2 : 2 * U * H * 2);
-      if (ch == 0) {
-        if (valid && (primal || htan)) load_row64(hB + ((size_t)(node0 + g) * ND + q) * H, v);
-        else {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] = 0.f;
-        }
-        st_a64(ahi_of(0), alo_of(0), v);
-      }
-      tc_sync();
-      if (warp == 0) { const uint32_t w = wq_wait(seq + 1); issue_mma(acc_of(0), ahi_of(0), alo_of(0), w, H, U, true, &mbar_mma[0]); }
-      wait_mma(0);
-      seq += 2;
-      // hidden layers: epilogue of layer l-1, then MMA with Wh[l] (l = 1..L-1), finally WhL
-      for (int l = 1; l <= L; ++l) {
-        // the buffer of the weights consumed two steps ago is free: prefetch the image after the next one
-        if (l + 1 <= L) wq_load(l + 1 < L ? ib.Wh[l + 1] : ib.WhL, l + 1 < L ? 2 * U * U * 2 : 2 * U * H * 2);
-        ld_acc64(acc_of(0), v);
-        act_rule(v, bp.bh[l - 1], valid, primal, g, nn);
-        st_a64(ahi_of(0), alo_of(0), v);
-        tc_sync();
-        if (warp == 0) {
-          const uint32_t w = wq_wait(seq);
-          issue_mma(acc_of(0), ahi_of(0), alo_of(0), w, U, l < L ? U : H, false, &mbar_mma[0]);
-        }
-        wait_mma(0);
-        ++seq;
-      }
-      if (ch == 0) {
-        ld_acc64(acc_of(0), v);
-        if (valid) {
-          float hres[64];
-          if (primal || htan) load_row64(hB + ((size_t)(node0 + g) * ND + q) * H, hres);
-          else {
-#pragma unroll
-            for (int c = 0; c < 64; ++c) hres[c] = 0.f;
-          }
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] += hres[c] + (primal ? bp.bh[L][c] : 0.f);
-          store_row64(hA + ((size_t)(node0 + g) * ND + q) * H, v);
-        }
-      }
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-    }
-  }
-
-  // =============================================================================================================
-  // edge phase
-  // =============================================================================================================
-  struct Tile {
-    int e0, ng, nrows;
-    bool active;
-  };
-
-  // per-edge geometry + per-row metadata of one tile into the slot's shared arrays (all threads; ends with a barrier)
-  __device__ __forceinline__ void tile_meta(int s, const Tile& t, int kind, int r) {
-    float* gvs = gv + s * TC_GMAX * 3;
-    if (t.active && tid < t.ng) {
-      const int e = t.e0 + tid, i = e / (n - 1), jj = e - i * (n - 1);
-      int j = i + 1 + jj; if (j >= n) j -= n;
-      float sq = 0.f;
-      for (int c = 0; c < dim; ++c) {
-        const float vv = xs[i * dim + c] - xs[j * dim + c];
-        gvs[tid * 3 + c] = vv;
-        sq = fmaf(vv, vv, sq);
-      }
-      const int isz = (sq == 0.f);
-      const float s1 = isz ? 1.f : sq;
-      const float len = sqrtf(s1);
-      gi[s * TC_GMAX + tid] = i; gj[s * TC_GMAX + tid] = j; giz[s * TC_GMAX + tid] = isz;
-      gs1[s * TC_GMAX + tid] = s1; glen[s * TC_GMAX + tid] = len; ginv[s * TC_GMAX + tid] = 1.f / (m.C + len);
-    }
-    __syncthreads();
-    if (t.active && tid < t.nrows) {
-      const int g = tid / r, q = tid - g * r;
-      rowgrp[s * 128 + tid] = g;
-      if (q == 0) {
-        rowslot[s * 128 + tid] = 0;
-        rowsd[s * 128 + tid] = gs1[s * TC_GMAX + g];
+    for (int c = 0; c < 64; ++c) {
+      const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+      if (pr) {
+        const float z = v[c] + bias;
+        const float sg = __fdividef(1.f, 1.f + __expf(-z));
+        cur = sg * (1.f + z * (1.f - sg));
+        v[c] = z * sg;
       } else {
-        const int i = gi[s * TC_GMAX + g], j = gj[s * TC_GMAX + g];
-        const int k = dirmap(kind, q - 1, i, j, dim);
-        float sd = 0.f;
-        for (int c = 0; c < dim; ++c) sd = fmaf(gvs[g * 3 + c], xt[(i * dim + c) * D + k] - xt[(j * dim + c) * D + k], sd);
-        rowslot[s * 128 + tid] = 1 + k;
-        rowsd[s * 128 + tid] = giz[s * TC_GMAX + g] ? 0.f : 2.f * sd;
+        v[c] *= cur;
       }
     }
-    __syncthreads();
+  }
+  template <int W>   // 2W partial sums -> W, exchanging with lane ^ (W/2)
+  __device__ __forceinline__ void bfly_round(float (&x)[32]) const {
+    const bool b = (lane & (W >> 1)) != 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const float keep = b ? x[W + i] : x[i], send = b ? x[i] : x[W + i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, W >> 1);
+    }
+  }
+  // column sums over the 32 features of this warp of v[c] * wf (transposing butterfly): lane l ends with the columns
+  // 2l and 2l+1 of its half, stored to pd[2l], pd[2l+1]
+  __device__ __forceinline__ void warp_dot(const float (&v)[64], float wf, float* pd) {
+    float x[32];
+    {
+      const bool b = (lane & 16) != 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float lo = v[i] * wf, hi = v[32 + i] * wf;
+        const float keep = b ? hi : lo, send = b ? lo : hi;
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    bfly_round<16>(x);
+    bfly_round<8>(x);
+    bfly_round<4>(x);
+    bfly_round<2>(x);
+    *reinterpret_cast<float2*>(pd + 2 * lane) = make_float2(x[0], x[1]);
+  }
+  // weight image (hi | lo, K x 128 lanes) -> TMEM columns [col, col + K)
+  template <int K>
+  __device__ __forceinline__ void load_w(int img_off, uint32_t col) {
+    constexpr int NC = K / 16;     // uint4 chunks per thread and part
+    const uint4* src = reinterpret_cast<const uint4*>(img.base + img_off);
+    uint32_t wv[2][NC * 4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const uint4 q = __ldg(src + (size_t)(p * (K / 8) + hh * NC + j) * 128 + f);
+        wv[p][4 * j] = q.x; wv[p][4 * j + 1] = q.y; wv[p][4 * j + 2] = q.z; wv[p][4 * j + 3] = q.w;
+      }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const uint32_t addr = tmem + col + lane_addr + (uint32_t)(p * (K / 2) + hh * (K / 4));
+      if constexpr (K == 128) tmem_st32(addr, wv[p]);
+      else tmem_st16(addr, wv[p]);
+    }
+    tmem_wait_st();
   }
 
-  // phi_e layer 0 by gather: z0 = P_s[j] + P_r[i] + (|v|^2 or its tangent) w_d.  Rows are fetched warp-per-row
-  // (coalesced 256 B segments), transposed through the staging buffer to the thread-per-row ownership, then the
-  // activation / tangent rule is applied and the A operand written.
-  __device__ __forceinline__ void tile_build(int s, const Tile& t, int r, bool htan, const float* wd) {
-    const bool valid = t.active && row < t.nrows;
-    const int g = valid ? rowgrp[s * 128 + row] : 0;
-    const bool primal = valid && (row == g * r);
-    const int lane = tid & 31;
-    float v[64];
-    qbeg();
-    for (int half = 0; half < 2; ++half) {
-      const float2 w2 = *reinterpret_cast<const float2*>(wd + 64 * half + 2 * lane);
-      // 8 rows per warp pass: all 16 global loads are issued before any of them is consumed
-      for (int r0 = warp; r0 < t.nrows; r0 += 8 * (NTHREADS / 32)) {
-        float2 pa[8], pb[8];
-        float sd[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int rr = r0 + u * (NTHREADS / 32);
-          pa[u] = make_float2(0.f, 0.f);
-          pb[u] = make_float2(0.f, 0.f);
-          sd[u] = 0.f;
-          if (rr < t.nrows) {
-            const int gg = rowgrp[s * 128 + rr];
-            sd[u] = rowsd[s * 128 + rr];
-            if (rr == gg * r || htan) {
-              const int slot = rowslot[s * 128 + rr];
-              pa[u] = *reinterpret_cast<const float2*>(Ps + ((size_t)gj[s * TC_GMAX + gg] * ND + slot) * U + 64 * half + 2 * lane);
-              pb[u] = *reinterpret_cast<const float2*>(Pr + ((size_t)gi[s * TC_GMAX + gg] * ND + slot) * U + 64 * half + 2 * lane);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int rr = r0 + u * (NTHREADS / 32);
-          if (rr < t.nrows) {
-            stage[rr * TC_SLD + 2 * lane] = fmaf(sd[u], w2.x, pa[u].x + pb[u].x);
-            stage[rr * TC_SLD + 2 * lane + 1] = fmaf(sd[u], w2.y, pa[u].y + pb[u].y);
-          }
-        }
-      }
-      __syncthreads();
-      if (ch == half) {
-        if (valid) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] = stage[row * TC_SLD + c];
-        } else {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) v[c] = 0.f;
-        }
-      }
-      __syncthreads();
-    }
-    qend(P_BUILD_GATHER);
-    act_rule(v, nullptr, valid, primal, g, t.ng);
-    st_a64(ahi_of(s), alo_of(s), v);
-    qend(P_BUILD_ACT);
+  // ---- tile tables ---------------------------------------------------------------------------------------------------
+  __device__ __forceinline__ const uint32_t* tile_ptr(int kind, int tile) const {
+    return a.tabs.base + (size_t)(a.tabs.off[kind] + tile) * TC_TILE_WORDS;
   }
+  __device__ __forceinline__ int tile_N(int kind, int tile) const { return (int)__ldg(tile_ptr(kind, tile) + 192 + TH_N); }
+  __device__ __forceinline__ int hdr(int s, int k) const { return TCI(hdr)[s * 16 + k]; }
 
-  // attention gate + message aggregation (egnn.py:99-104) from the fp32 phi_e outputs of this tile (all of whose edges
-  // share one receiver).  v = this thread's 64 columns of m (primal) / m-dot (tangent).  All threads.
-  __device__ __forceinline__ void tile_messages(int s, const Tile& t, int kind, int r, const float (&v)[64], const float* wa,
-                                float bav) {
-    const bool valid = row < t.nrows;
-    const float inv_sqrt_nb = rsqrtf((float)(n - 1));
-    const int i = gi[s * TC_GMAX];
-    qbeg();
-    rdot[(s * 2 + ch) * 128 + row] = valid ? dot64(v, wa) : 0.f;
-    __syncthreads();
-    qend(P_MSG_DOT);
-    if (tid < t.ng)
-      ge[s * TC_GMAX + tid] = ecnf_sigmoid(rdot[(s * 2) * 128 + tid * r] + rdot[(s * 2 + 1) * 128 + tid * r] + bav);
-    // two passes over the column halves through the staging buffer [128 rows][65]
-    for (int half = 0; half < 2; ++half) {
-      __syncthreads();
-      if (ch == half && valid) {
+  // =============================================================================================================
+  // The software pipeline shared by the three phases.  P provides
+  //   ntiles, NL (layers per tile), kind (tile table), stream (weights streamed layer by layer through two buffers)
+  //   prologue()                  epilogue threads, before the first tile
+  //   build(s, tile)              epilogue threads: first B operand of the tile
+  //   epi(s, tile, w)             epilogue threads: consume the accumulator of layer w (and write the next B operand)
+  //   wload(w, col)               epilogue threads: weights of layer w -> TMEM columns col (stream only)
+  //   a_col(q, w), K(w)           MMA operand position / depth for layer w at stream position q
+  // =============================================================================================================
+  template <class P>
+  __device__ __forceinline__ void run_phase(P& p) {
+    const int ntiles = p.ntiles, NL = p.NL;
+    const int npairs = (ntiles + 1) >> 1;
+    const int total_q = npairs * NL;
+    if (is_epi) {
+      p.prologue();
+      if (p.stream) {
+        p.wload(0, TC_WCOL);
+        if (total_q > 1) p.wload(1 % NL, TC_WCOL + 128);
+      }
+    }
 #pragma unroll
-        for (int c = 0; c < 64; ++c) stage[row * TC_SLD + c] = v[c];
-      }
-      __syncthreads();
-      qend(P_MSG_STAGE);
-      // message rows  msg = m e,  msg-dot = m-dot e + m e(1-e)(m-dot . wa)  are formed on the fly inside the segmented
-      // sums over the edges of this receiver; thread -> (column c, row-in-group q), lanes run over consecutive columns
-      for (int idx = tid; idx < r * 64; idx += NTHREADS) {
-        const int c = idx & 63, q = idx >> 6;
-        const int col = 64 * half + c;
-        const bool shared_q = (q == 0) || kind == KIND_MID || (q - 1 < dim);
-        float acc = 0.f;
-        for (int g = 0; g < t.ng; ++g) {
-          const float e = ge[s * TC_GMAX + g];
-          const float mp = stage[g * r * TC_SLD + c];
-          float x;
-          if (q == 0) {
-            x = mp * e;
-          } else {
-            const int rr = g * r + q;
-            const float ed = e * (1.f - e) * (rdot[(s * 2) * 128 + rr] + rdot[(s * 2 + 1) * 128 + rr]);
-            x = fmaf(mp, ed, stage[rr * TC_SLD + c] * e);
-          }
-          if (shared_q) acc += x;
-          else macc[(1 + gj[s * TC_GMAX + g] * dim + (q - 1 - dim)) * U + col] += x * inv_sqrt_nb;
-        }
-        if (shared_q) {
-          const int slot = (q == 0) ? 0 : 1 + dirmap(kind, q - 1, i, 0, dim);
-          macc[slot * U + col] += acc * inv_sqrt_nb;
-        }
-      }
+    for (int s = 0; s < 2; ++s) {
+      if (s >= ntiles) continue;
+      if (is_epi) { p.build(s, s); arrive_ready(s); }
+      else { ctrl_wait_ready(s); issue_mma(s, p.a_col(0, 0), p.K(0), tile_N(p.kind, s)); }
     }
-    __syncthreads();
-    qend(P_MSG_SEG);
-    // receiver complete -> flush its aggregate to global (coalesced) and clear the accumulator
-    if (t.e0 + t.ng == (i + 1) * (n - 1)) {
-      for (int idx = tid; idx < ND * U; idx += NTHREADS) {
-        Mg[(size_t)i * ND * U + idx] = macc[idx];
-        macc[idx] = 0.f;
-      }
-      __syncthreads();
-    }
-    qend(P_MSG_FLUSH);
-  }
-
-  // coordinate update (egnn.py:87-95) from the head outputs p (rdot) of one tile.  All threads; ends with a barrier.
-  __device__ __forceinline__ void tile_coords(int s, const Tile& t, int kind, int r, float bpv) {
-    if (t.active) {
-      const float* gvs = gv + s * TC_GMAX * 3;
-      const int i_first = gi[s * TC_GMAX], i_last = gi[s * TC_GMAX + t.ng - 1];
-      const int nrec = i_last - i_first + 1;
-      const int per = dim + (r - 1) * dim;   // primal + tangent work items per receiver
-      for (int idx = tid; idx < nrec * per; idx += NTHREADS) {
-        const int ri = idx / per, w = idx - ri * per, i = i_first + ri;
-        const int ga = max(t.e0, i * (n - 1)) - t.e0, gb = min(t.e0 + t.ng, (i + 1) * (n - 1)) - t.e0;
-        if (w < dim) {
-          const int c = w;
-          float acc = 0.f;
-          for (int g = ga; g < gb; ++g) {
-            const float pg = rdot[(s * 2) * 128 + g * r] + rdot[(s * 2 + 1) * 128 + g * r] + bpv;
-            acc = fmaf(pg * gvs[g * 3 + c], ginv[s * TC_GMAX + g], acc);
-          }
-          xacc[i * dim + c] += acc;
-        } else {
-          const int t2 = w - dim, q = 1 + t2 / dim, c = t2 % dim;
-          for (int g = ga; g < gb; ++g) {
-            const int j = gj[s * TC_GMAX + g];
-            const int k = dirmap(kind, q - 1, i, j, dim);
-            if (kind == KIND_LAST && k != i * dim + c) continue;
-            const int rr = g * r + q;
-            const float pg = rdot[(s * 2) * 128 + g * r] + rdot[(s * 2 + 1) * 128 + g * r] + bpv;
-            const float pd = rdot[(s * 2) * 128 + rr] + rdot[(s * 2 + 1) * 128 + rr];
-            const float vc = gvs[g * 3 + c], inv = ginv[s * TC_GMAX + g];
-            const float vd = xt[(i * dim + c) * D + k] - xt[(j * dim + c) * D + k];
-            const float ld = giz[s * TC_GMAX + g] ? 0.f : rowsd[s * 128 + rr] / (2.f * glen[s * TC_GMAX + g]);
-            const float cd = (pd * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
-            if (kind == KIND_LAST) dacc[i * dim + c] += cd;
-            else xtacc[(i * dim + c) * D + k] += cd;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  __device__ __forceinline__ void edge_phase(int b, int kind, bool htan) {
-    const EcnfBlockParams& bp = m.blk[b];
-    const TcImgBlock& ib = img.blk[b];
-    const int L = m.L;
-    const int nact = kind == KIND_MID ? D : kind == KIND_LAST ? dim : 2 * dim;
-    const int r = 1 + nact;
-    // tiles hold whole edges; when messages are aggregated (not the last block) a tile never spans two receivers
-    const int gpt = (kind == KIND_LAST) ? min(128 / r, TC_GMAX) : min(min(128 / r, TC_GMAX), n - 1);
-    const int tpr = (n - 1 + gpt - 1) / gpt;                       // tiles per receiver (non-last blocks)
-    const int ntiles = (kind == KIND_LAST) ? (E + gpt - 1) / gpt : n * tpr;
-    const int NW = 2 * L - 1;                  // We[1..L-1], Wx[0..L-1]
-    const float* wd = bp.We[0] + (size_t)2 * H * U;
-    const float bpv = bp.bp[0], bav = bp.ba[0];
-    pbeg();
-    for (int i = tid; i < D; i += NTHREADS) { xacc[i] = 0.f; dacc[i] = 0.f; }
-    if (kind != KIND_LAST) {
-      for (int i = tid; i < D * D; i += NTHREADS) xtacc[i] = 0.f;
-      for (int i = tid; i < ND * U; i += NTHREADS) macc[i] = 0.f;
-    }
-    auto wimg = [&](int w) { return w < L - 1 ? ib.We[w + 1] : ib.Wx[w - (L - 1)]; };
-    // per-block vectors live in shared memory for the whole phase (the L1 is too small to keep them: 217 KB carve-out)
-    for (int idx = tid; idx < (NW + 3) * U; idx += NTHREADS) {
-      const int w = idx / U, c = idx - w * U;
-      const float* src = w < L - 1 ? bp.be[w + 1] : w < NW ? bp.bx[w - (L - 1)] : w == NW ? wd : w == NW + 1 ? bp.wa : bp.wp;
-      vecs[idx] = src[c];
-    }
-    auto wbias = [&](int w) { return vecs + w * U; };
-    const float* wd_s = vecs + NW * U;
-    const float* wa_s = vecs + (NW + 1) * U;
-    const float* wp_s = vecs + (NW + 2) * U;
-    const int npairs = (ntiles + 1) / 2;
-    const uint32_t seq_base = wq_head;
-    const uint32_t seq_end = seq_base + (uint32_t)(npairs * NW);
-    wq_load(wimg(0), 2 * U * U * 2);
-    if (seq_base + 1 < seq_end) wq_load(wimg(1 % NW), 2 * U * U * 2);
-    __syncthreads();
-    pend(P_EDGE_INIT);
-
-    for (int p = 0; p < npairs; ++p) {
-      Tile t[2];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int ti = 2 * p + s;
-        t[s].active = ti < ntiles;
-        if (kind == KIND_LAST) {
-          t[s].e0 = ti * gpt;
-          t[s].ng = t[s].active ? min(gpt, E - t[s].e0) : 0;
-        } else {
-          const int i = ti / tpr, k = ti - i * tpr;
-          t[s].e0 = i * (n - 1) + k * gpt;
-          t[s].ng = t[s].active ? min(gpt, (n - 1) - k * gpt) : 0;
-        }
-        t[s].nrows = t[s].ng * r;
-      }
-      const uint32_t seq0 = seq_base + (uint32_t)(p * NW);
-      // stage 0: build both tiles and start their first GEMM
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (!t[s].active) continue;
-        pbeg();
-        tile_meta(s, t[s], kind, r);
-        pend(P_META);
-        tile_build(s, t[s], r, htan, wd_s);
-        pend(P_BUILD);
-        tc_sync();
-        if (warp == 0) { const uint32_t w = wq_wait(seq0); issue_mma(acc_of(s), ahi_of(s), alo_of(s), w, U, U, false, &mbar_mma[s]); }
-        pend(P_SYNC_ISSUE);
-      }
-      for (int w = 0; w < NW; ++w) {
+    int q = 0;
+    for (int pr = 0; pr < npairs; ++pr) {
+      for (int w = 0; w < NL; ++w, ++q) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          if (!t[s].active) continue;
-          pbeg();
-          wait_mma(s);
-          pend(P_WAIT_MMA);
-          // after the LAST active slot finished with weights `w`, their buffer is free: prefetch two images ahead
-          const bool last_slot = (s == 1) || !t[1].active;
-          if (last_slot && seq0 + w + 2 < seq_end) wq_load(wimg((w + 2) % NW), 2 * U * U * 2);
-          const bool valid = row < t[s].nrows;
-          const int g = valid ? rowgrp[s * 128 + row] : 0;
-          const bool primal = valid && (row == g * r);
-          float v[64];
-          qbeg();
-          ld_acc64(acc_of(s), v);
-          qend(P_EPI_LD);
-          act_rule(v, wbias(w), valid, primal, g, t[s].ng);
-          qend(P_EPI_ACT);
-          if (w < NW - 1) {
-            st_a64(ahi_of(s), alo_of(s), v);
-            qend(P_EPI_ST);
-            pend(P_EPI);
-            if (w == L - 2 && kind != KIND_LAST) tile_messages(s, t[s], kind, r, v, wa_s, bav);
-            pend(P_MSG);
-            tc_sync();
-            if (warp == 0) {
-              const uint32_t wsm = wq_wait(seq0 + w + 1);
-              issue_mma(acc_of(s), ahi_of(s), alo_of(s), wsm, U, U, false, &mbar_mma[s]);
-            }
-            pend(P_SYNC_ISSUE);
+          const int tile = 2 * pr + s;
+          if (tile >= ntiles) continue;
+          const bool last_slot = (s == 1) || (tile + 1 >= ntiles);
+          const int ntile = tile + 2;
+          if (is_epi) {
+            wait_done(s);
+            if (p.stream && last_slot && q + 2 < total_q) { qbeg(); p.wload((w + 2) % NL, TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
+            p.epi(s, tile, w);
+            if (w < NL - 1) arrive_ready(s);
+            else if (ntile < ntiles) { p.build(s, ntile); arrive_ready(s); }
           } else {
-            rdot[(s * 2 + ch) * 128 + row] = valid ? dot64(v, wp_s) : 0.f;
-            tc_fence_before();
-            __syncthreads();
-            tc_fence_after();
-            pend(P_EPI);
-            tile_coords(s, t[s], kind, r, bpv);
-            pend(P_COORDS);
+            if (w < NL - 1) { ctrl_wait_ready(s); issue_mma(s, p.a_col(q + 1, w + 1), p.K(w + 1), tile_N(p.kind, tile)); }
+            else if (ntile < ntiles) { ctrl_wait_ready(s); issue_mma(s, p.a_col(q + 1, 0), p.K(0), tile_N(p.kind, ntile)); }
           }
         }
       }
     }
   }
+
+  // column metadata of a node tile (kinds TT_NODE1 / TT_NODE): row offset (node * ND + slot), primal masks, header
+  __device__ __forceinline__ void node_meta(int s, int kind, int tile) {
+    qbeg();
+    epi_bar();     // every thread is done with the previous contents of slot s's metadata
+    const uint32_t* tp = tile_ptr(kind, tile);
+    if (tid < 128) {
+      const uint32_t w = __ldg(tp + tid);
+      TCW(colw)[s * 128 + tid] = w;
+      TCI(coloffR)[s * 128 + tid] = (w & CW_VALID) ? cw_gid(w) * ND + cw_q(w) : -1;
+      const uint32_t bal = __ballot_sync(0xffffffffu, (w & CW_PRIMAL) != 0u);
+      if (lane == 0) TCW(pm)[s * 4 + warp] = bal;
+    } else if (tid < 144) {
+      TCW(hdr)[s * 16 + (tid - 128)] = __ldg(tp + 192 + (tid - 128));
+    }
+    epi_bar();
+    qend(P_META);
+  }
+
+  // =============================================================================================================
+  // node phase 1: h_in = [h | tau] Wd + bd ; P_s = h_in We0[0:H] ; P_r = h_in We0[H:2H] + be0 ; P_h = h_in Wh0[U:U+H] + bh0
+  // =============================================================================================================
+  struct NodePre {
+    EngineTC& e;
+    int b, ntiles, NL, kind;
+    static constexpr bool stream = false;
+    __device__ __forceinline__ uint32_t a_col(int, int w) const { return TC_WCOL + 64u * w; }
+    __device__ __forceinline__ int K(int) const { return TCH; }
+    __device__ __forceinline__ void wload(int, uint32_t) {}
+    __device__ __forceinline__ void prologue() {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      const TcImgBlock& ib = e.img.blk[b];
+      if (e.tid < TCH) {
+        float cv = bp.bd[e.tid];
+        for (int k = 0; k < e.m.T; ++k) cv = fmaf(TCF(tau)[k], bp.Wd[(TCH + k) * TCH + e.tid], cv);
+        TCF(cvec)[e.tid] = cv;
+      }
+      e.template load_w<TCH>(ib.Wd, TC_WCOL);
+      e.template load_w<TCH>(ib.We0s, TC_WCOL + 64);
+      e.template load_w<TCH>(ib.We0r, TC_WCOL + 128);
+      if (NL > 3) e.template load_w<TCH>(ib.Wh0h, TC_WCOL + 192);
+    }
+    __device__ __forceinline__ void build(int s, int tile) {
+      const KernelArgs& a = e.a;
+      e.node_meta(s, kind, tile);
+      float v[64];
+      const float* src = e.hA();
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
+        v[c] = (ro >= 0 && e.f < TCH) ? src[(size_t)ro * TCH + e.f] : 0.f;
+      }
+      if (e.f < TCH) e.write_B(s, v);
+    }
+    __device__ __forceinline__ void epi(int s, int, int w) {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      float v[64];
+      e.ld_acc(s, v);
+      const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
+      if (w == 0) {
+        if (e.f < TCH) {
+          const float cv = TCF(cvec)[e.f];
+          float* dst = e.hB();
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+            if (pr) v[c] += cv;
+            const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
+            if (ro >= 0) dst[(size_t)ro * TCH + e.f] = v[c];    // a repeated primal column rewrites the same value
+          }
+          e.write_B(s, v);
+        }
+      } else {
+        const float bias = w == 1 ? 0.f : (w == 2 ? bp.be[0][e.f] : bp.bh[0][e.f]);
+        float* dst = w == 1 ? e.Ps() : (w == 2 ? e.Pr() : e.Ph());
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+          const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
+          if (ro >= 0) dst[(size_t)ro * TCU + e.f] = pr ? v[c] + bias : v[c];
+        }
+      }
+    }
+  };
+
+  // =============================================================================================================
+  // node phase 2: h <- phi_h([M | h_in]) + h_in        (the h_in part of layer 0 is P_h from phase 1)
+  // =============================================================================================================
+  struct NodePost {
+    EngineTC& e;
+    int b, ntiles, NL, kind;
+    bool htan;
+    static constexpr bool stream = true;
+    __device__ __forceinline__ uint32_t a_col(int q, int) const { return TC_WCOL + 128u * (q & 1); }
+    __device__ __forceinline__ int K(int) const { return TCU; }
+    __device__ __forceinline__ void prologue() {}
+    __device__ __forceinline__ void wload(int w, uint32_t col) {
+      const TcImgBlock& ib = e.img.blk[b];
+      const int L = e.m.L;
+      e.template load_w<TCU>(w == 0 ? ib.Wh0m : (w < L ? ib.Wh[w] : ib.WhL), col);
+    }
+    __device__ __forceinline__ void build(int s, int tile) {
+      const KernelArgs& a = e.a;
+      e.node_meta(s, kind, tile);
+      float v[64];
+      const float* src = e.Mg();
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
+        v[c] = src[(size_t)(ro >= 0 ? ro : 0) * TCU + e.f];
+        if (ro < 0) v[c] = 0.f;
+      }
+      e.write_B(s, v);
+    }
+    __device__ __forceinline__ void epi(int s, int, int w) {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      const int L = e.m.L;
+      float v[64];
+      if (w == 0) {
+        // issue the P_h loads before the accumulator arrives in registers
+        const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
+        const float* ph = e.Ph();
+        float pv[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+          const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
+          const bool use = ro >= 0 && (pr || htan);
+          pv[c] = ph[(size_t)(use ? ro : 0) * TCU + e.f];
+          if (!use) pv[c] = 0.f;
+        }
+        e.ld_acc(s, v);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) v[c] += pv[c];
+        e.act_rule(v, 0.f, s);
+        e.write_B(s, v);
+      } else if (w < L) {
+        const float bias = bp.bh[w][e.f];
+        e.ld_acc(s, v);
+        e.act_rule(v, bias, s);
+        e.write_B(s, v);
+      } else {
+        e.ld_acc(s, v);
+        if (e.f < TCH) {
+          const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
+          const float bias = bp.bh[L][e.f];
+          const float* hin = e.hB();
+          float* dst = e.hA();
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+            const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
+            if (ro >= 0) {
+              float x = v[c];
+              if (pr) x += bias;
+              if (pr || htan) x += hin[(size_t)ro * TCH + e.f];
+              dst[(size_t)ro * TCH + e.f] = x;
+            }
+          }
+        }
+      }
+    }
+  };
+
+  // =============================================================================================================
+  // edge phase: phi_e (layer 0 by gather) -> {attention gate + message aggregation, phi_x -> coordinate update}
+  // =============================================================================================================
+  struct EdgePh {
+    EngineTC& e;
+    int b, ntiles, NL, kind;   // kind = tile table (TT_FIRST / TT_MID / TT_LAST)
+    bool htan;
+    float wdf, waf, wpf;       // my feature's entry of w_d (|v|^2 column of phi_e layer 0), attention and head weights
+    static constexpr bool stream = true;
+    __device__ __forceinline__ uint32_t a_col(int q, int) const { return TC_WCOL + 128u * (q & 1); }
+    __device__ __forceinline__ int K(int) const { return TCU; }
+    __device__ __forceinline__ int ekind() const { return kind == TT_FIRST ? KIND_FIRST : kind == TT_MID ? KIND_MID : KIND_LAST; }
+    __device__ __forceinline__ void wload(int w, uint32_t col) {
+      const TcImgBlock& ib = e.img.blk[b];
+      const int L = e.m.L;
+      e.template load_w<TCU>(w < L - 1 ? ib.We[w + 1] : ib.Wx[w - (L - 1)], col);
+    }
+    __device__ __forceinline__ void prologue() {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      const int n = e.n, dim = e.dim, D = e.D;
+      wdf = bp.We[0][(size_t)2 * TCH * TCU + e.f];
+      waf = bp.wa[e.f];
+      wpf = bp.wp[e.f];
+      for (int i = e.tid; i < D; i += TC_EPI) { TCF(xacc)[i] = 0.f; TCF(dacc)[i] = 0.f; }
+      if (kind != TT_LAST) {
+        for (int i = e.tid; i < D * D; i += TC_EPI) TCF(xtacc)[i] = 0.f;
+        for (int i = e.tid; i < 2 * a.lay.mrows * TCU; i += TC_EPI) TCF(macc)[i] = 0.f;
+      }
+      // per-edge geometry (egnn.py:73-76, numerical.py:7-10)
+      for (int ed = e.tid; ed < e.E; ed += TC_EPI) {
+        const int i = ed / (n - 1), jj = ed - i * (n - 1);
+        int j = i + 1 + jj; if (j >= n) j -= n;
+        float sq = 0.f;
+        for (int c = 0; c < dim; ++c) {
+          const float vv = TCF(xs)[i * dim + c] - TCF(xs)[j * dim + c];
+          TCF(egv)[ed * 3 + c] = vv;
+          sq = fmaf(vv, vv, sq);
+        }
+        const int isz = (sq == 0.f);
+        const float s1 = isz ? 1.f : sq;
+        const float len = sqrtf(s1);
+        TCI(egiz)[ed] = isz; TCF(egs1)[ed] = s1; TCF(eglen)[ed] = len; TCF(eginv)[ed] = 1.f / (e.m.C + len);
+      }
+      // the first tile's metadata pass starts with a barrier
+    }
+    // per-column metadata of an edge tile
+    __device__ __forceinline__ void meta(int s, int tile) {
+      const KernelArgs& a = e.a;
+      const int n = e.n, dim = e.dim, D = e.D, ND = e.ND;
+      e.qbeg();
+      e.epi_bar();
+      const uint32_t* tp = e.tile_ptr(kind, tile);
+      if (e.tid < 128) {
+        const uint32_t w = __ldg(tp + e.tid);
+        const int win = (int)__ldg(tp + 192 + TH_WIN);
+        int oS = -1, oR = 0, mr = -1;
+        float sd = 0.f;
+        if (w & CW_VALID) {
+          const int ed = cw_gid(w), q = cw_q(w);
+          const int i = ed / (n - 1), jj = ed - i * (n - 1);
+          int j = i + 1 + jj; if (j >= n) j -= n;
+          int slot = 0;
+          if (q == 0) {
+            sd = TCF(egs1)[ed];
+          } else {
+            const int k = dirmap(ekind(), q - 1, i, j, dim);
+            slot = 1 + k;
+            float acc = 0.f;
+            for (int c = 0; c < dim; ++c)
+              acc = fmaf(TCF(egv)[ed * 3 + c], TCF(xt)[(i * dim + c) * D + k] - TCF(xt)[(j * dim + c) * D + k], acc);
+            sd = TCI(egiz)[ed] ? 0.f : 2.f * acc;
+          }
+          if (q == 0 || htan) { oS = (j * ND + slot) * TCU; oR = (i * ND + slot) * TCU; }
+          if (!(w & CW_DUP)) mr = ((i - win) * ND + slot) * TCU;
+        }
+        TCW(colw)[s * 128 + e.tid] = w;
+        TCI(coloffS)[s * 128 + e.tid] = oS;
+        TCI(coloffR)[s * 128 + e.tid] = oR;
+        TCF(colsd)[s * 128 + e.tid] = sd;
+        TCI(colmrow)[s * 128 + e.tid] = mr;
+        const uint32_t bal = __ballot_sync(0xffffffffu, (w & CW_PRIMAL) != 0u);
+        if (e.lane == 0) TCW(pm)[s * 4 + e.warp] = bal;
+      } else if (e.tid < 192) {
+        TCW(grpw)[s * 64 + (e.tid - 128)] = __ldg(tp + e.tid);
+      } else if (e.tid < 208) {
+        TCW(hdr)[s * 16 + (e.tid - 192)] = __ldg(tp + e.tid);
+      }
+      e.epi_bar();
+      e.qend(P_META);
+    }
+    // phi_e layer 0 by gather: z0 = P_s[j] + P_r[i] + (|v|^2 or its tangent) w_d, then the activation rule
+    __device__ __forceinline__ void build(int s, int tile) {
+      const KernelArgs& a = e.a;
+      meta(s, tile);
+      e.qbeg();
+      float v[64];
+      const float* ps = e.Ps() + e.f;
+      const float* pr = e.Pr() + e.f;
+#pragma unroll
+      for (int cb = 0; cb < 64; cb += 16) {
+        float pa[16], pb[16];
+        int os[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int col = s * 128 + 64 * e.hh + cb + u;
+          os[u] = TCI(coloffS)[col];
+          const int orr = TCI(coloffR)[col];
+          pa[u] = ps[os[u] >= 0 ? os[u] : 0];
+          pb[u] = pr[orr];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float sd = TCF(colsd)[s * 128 + 64 * e.hh + cb + u];
+          v[cb + u] = os[u] >= 0 ? fmaf(sd, wdf, pa[u] + pb[u]) : sd * wdf;
+        }
+      }
+      e.act_rule(v, 0.f, s);
+      e.write_B(s, v);
+      e.qend(P_BUILD);
+    }
+    __device__ __forceinline__ void epi(int s, int tile, int w) {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      const int L = e.m.L;
+      const float bias = w < L - 1 ? bp.be[w + 1][e.f] : bp.bx[w - (L - 1)][e.f];
+      float v[64];
+      e.qbeg();
+      e.ld_acc(s, v);
+      e.act_rule(v, bias, s);
+      if (w < NL - 1) {
+        e.write_B(s, v);
+        e.qend(P_EPI);
+        if (w == L - 2 && kind != TT_LAST) messages(s, v);
+        e.qend(P_MSG);
+      } else {
+        e.qend(P_EPI);
+        coords(s, v);
+        e.qend(P_COORD);
+      }
+    }
+    // attention gate + message aggregation (egnn.py:99-104) from the fp32 phi_e outputs in v
+    __device__ __forceinline__ void messages(int s, const float (&v)[64]) {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      const int hh = e.hh, lane = e.lane, warp = e.warp;
+      float* pd = TCF(pdot) + s * 512;
+      e.warp_dot(v, waf, pd + warp * 64);
+      e.epi_bar();
+      {
+        const float bav = bp.ba[0];
+        const float* p4 = pd + (4 * hh) * 64;
+        float aco[2], bco[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = 2 * lane + u;
+          const uint32_t cw = TCW(colw)[s * 128 + 64 * hh + c];
+          const int pc = cw_pc(cw);
+          const float raw = (p4[c] + p4[64 + c]) + (p4[128 + c] + p4[192 + c]);
+          const float rawp = (p4[pc] + p4[64 + pc]) + (p4[128 + pc] + p4[192 + pc]);
+          const float eg = ecnf_sigmoid(rawp + bav);
+          aco[u] = eg;
+          bco[u] = (cw & CW_PRIMAL) ? 0.f : eg * (1.f - eg) * raw;
+        }
+        *reinterpret_cast<float2*>(TCF(wA) + warp * 64 + 2 * lane) = make_float2(aco[0], aco[1]);
+        *reinterpret_cast<float2*>(TCF(wB) + warp * 64 + 2 * lane) = make_float2(bco[0], bco[1]);
+      }
+      __syncwarp();
+      {
+        // msg = m e,  msg-dot = m-dot e + m e (1 - e) (m-dot . wa)   accumulated per (receiver, slot) row
+        float* mac = TCF(macc) + (size_t)hh * a.lay.mrows * TCU + e.f;
+        const float* wa_ = TCF(wA) + warp * 64;
+        const float* wb_ = TCF(wB) + warp * 64;
+        const uint32_t m0 = TCW(pm)[s * 4 + 2 * hh], m1 = TCW(pm)[s * 4 + 2 * hh + 1];
+        float curm = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+          if (pr) curm = v[c];
+          const int mr = TCI(colmrow)[s * 128 + 64 * hh + c];
+          if (mr >= 0) {
+            const float x = fmaf(curm, wb_[c], v[c] * wa_[c]);
+            mac[mr] += x;
+          }
+        }
+      }
+      if (e.hdr(s, TH_FLUSH)) {
+        // the receiver window is complete: write its aggregate to global (coalesced) and clear the accumulators
+        e.epi_bar();
+        const int win = e.hdr(s, TH_WIN);
+        const int nrecv = min(a.lay.mrows / e.ND, e.n - win);
+        const int rows = nrecv * e.ND;
+        const float inv_sqrt_nb = rsqrtf((float)(e.n - 1));
+        float* m0p = TCF(macc) + e.f;
+        float* m1p = m0p + (size_t)a.lay.mrows * TCU;
+        float* dst = e.Mg() + (size_t)win * e.ND * TCU + e.f;
+        for (int rr = hh; rr < rows; rr += 2) {
+          dst[(size_t)rr * TCU] = (m0p[rr * TCU] + m1p[rr * TCU]) * inv_sqrt_nb;
+          m0p[rr * TCU] = 0.f;
+          m1p[rr * TCU] = 0.f;
+        }
+      }
+    }
+    // coordinate head + coordinate update (egnn.py:82-95) and its tangents
+    __device__ __forceinline__ void coords(int s, const float (&v)[64]) {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      const int n = e.n, dim = e.dim, D = e.D;
+      const int ek = ekind();
+      float* pd = TCF(pdot) + s * 512;
+      e.warp_dot(v, wpf, pd + e.warp * 64);
+      e.epi_bar();
+      const float bpv = bp.bp[0];
+      float* cd = TCF(cdbuf) + s * 384;
+      for (int idx = e.tid; idx < 128 * dim; idx += TC_EPI) {
+        const int col = idx / dim, cc = idx - col * dim;
+        const uint32_t cw = TCW(colw)[s * 128 + col];
+        float val = 0.f;
+        if ((cw & CW_VALID) && !(cw & CW_DUP)) {
+          const int ed = cw_gid(cw), q = cw_q(cw);
+          const int i = ed / (n - 1), jj = ed - i * (n - 1);
+          int j = i + 1 + jj; if (j >= n) j -= n;
+          const float* p4 = pd + (4 * (col >> 6)) * 64;
+          const int cl = col & 63, pc = cw_pc(cw);
+          const float pg = (p4[pc] + p4[64 + pc]) + (p4[128 + pc] + p4[192 + pc]) + bpv;
+          const float vc = TCF(egv)[ed * 3 + cc], inv = TCF(eginv)[ed];
+          if (q == 0) {
+            val = pg * vc * inv;
+          } else {
+            const int k = dirmap(ek, q - 1, i, j, dim);
+            if (ek != KIND_LAST || k == i * dim + cc) {
+              const float pdv = (p4[cl] + p4[64 + cl]) + (p4[128 + cl] + p4[192 + cl]);
+              const float vd = TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k];
+              const float ld = TCI(egiz)[ed] ? 0.f : TCF(colsd)[s * 128 + col] / (2.f * TCF(eglen)[ed]);
+              val = (pdv * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
+            }
+          }
+        }
+        cd[col * 3 + cc] = val;
+      }
+      e.epi_bar();
+      {
+        const int r = ek == KIND_MID ? e.ND : ek == KIND_LAST ? 1 + dim : 1 + 2 * dim;
+        const int g0 = e.hdr(s, TH_G0), ng = e.hdr(s, TH_NG), i_first = e.hdr(s, TH_IFIRST), i_last = e.hdr(s, TH_ILAST);
+        const int per = r * dim;
+        for (int idx = e.tid; idx < (i_last - i_first + 1) * per; idx += TC_EPI) {
+          const int ri = idx / per, rem = idx - ri * per, q = rem / dim, cc = rem - q * dim;
+          const int i = i_first + ri;
+          if (ek == KIND_LAST && q != 0 && q - 1 != cc) continue;
+          const int ga = max(g0, i * (n - 1)) - g0, gb = min(g0 + ng, (i + 1) * (n - 1)) - g0;
+          const bool per_sender = (ek == KIND_FIRST && q > dim);
+          float acc = 0.f;
+          for (int lg = ga; lg < gb; ++lg) {
+            const uint32_t gw = TCW(grpw)[s * 64 + lg];
+            const int qsplit = (int)(gw & 255u), colA = (int)((gw >> 8) & 255u), colB = (int)((gw >> 16) & 255u);
+            const int col = q < qsplit ? colA + q : colB + 1 + (q - qsplit);
+            const float val = cd[col * 3 + cc];
+            if (per_sender) {
+              const int ed = g0 + lg, jj = ed - i * (n - 1);
+              int j = i + 1 + jj; if (j >= n) j -= n;
+              TCF(xtacc)[(i * dim + cc) * D + j * dim + (q - 1 - dim)] += val;
+            } else {
+              acc += val;
+            }
+          }
+          if (q == 0) TCF(xacc)[i * dim + cc] += acc;
+          else if (ek == KIND_LAST) TCF(dacc)[i * dim + cc] += acc;
+          else if (!per_sender) TCF(xtacc)[(i * dim + cc) * D + (ek == KIND_MID ? q - 1 : i * dim + q - 1)] += acc;
+        }
+      }
+    }
+  };
 
   // ---- one evaluation of (f, div f) at time t for the positions in xin (shared memory, D floats) ----
   __device__ __forceinline__ void eval(float t, const float* xin, const int32_t* feat, float* fout) {
-    if (tid < dim) {
-      float s = 0.f;
-      for (int i = 0; i < n; ++i) s += xin[i * dim + tid];
-      mu[tid] = s / (float)n;
+    if (is_epi) {
+      if (tid < dim) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += xin[i * dim + tid];
+        TCF(mu)[tid] = s / (float)n;
+      }
+      if (tid >= 32 && tid < 32 + m.T / 2) {
+        const int k = tid - 32;
+        const float arg = (t * 1000.f) * m.freqs[k];
+        TCF(tau)[k] = sinf(arg);
+        TCF(tau)[k + m.T / 2] = cosf(arg);
+      }
+      epi_bar();
+      for (int i = tid; i < D; i += TC_EPI) {
+        const float v = xin[i] - TCF(mu)[i % dim];
+        TCF(xs)[i] = v;
+        TCF(xs0)[i] = v;
+      }
+      const float invn = 1.f / (float)n;
+      for (int idx = tid; idx < D * D; idx += TC_EPI) {
+        const int ra = idx / D, k = idx - ra * D;
+        const int ia = ra / dim, ca = ra - ia * dim, ik = k / dim, ck = k - ik * dim;
+        TCF(xt)[idx] = (ca == ck) ? ((ia == ik ? 1.f : 0.f) - invn) : 0.f;
+      }
+      float* h0 = hA();
+      for (int idx = tid; idx < n * H; idx += TC_EPI) {
+        const int node = idx / H, col = idx - node * H;
+        int ft = feat[node];
+        ft = max(0, min(m.nfeat - 1, ft));
+        h0[(size_t)node * ND * H + col] = m.embed[ft * H + col];
+      }
+      epi_bar();
     }
-    if (tid >= 32 && tid < 32 + m.T / 2) {
-      const int k = tid - 32;
-      const float arg = (t * 1000.f) * m.freqs[k];
-      tau[k] = sinf(arg);
-      tau[k + m.T / 2] = cosf(arg);
-    }
-    __syncthreads();
-    for (int i = tid; i < D; i += NTHREADS) {
-      const float v = xin[i] - mu[i % dim];
-      xs[i] = v;
-      xs0[i] = v;
-    }
-    const float invn = 1.f / (float)n;
-    for (int idx = tid; idx < D * D; idx += NTHREADS) {
-      const int ra = idx / D, k = idx - ra * D;
-      const int ia = ra / dim, ca = ra - ia * dim, ik = k / dim, ck = k - ik * dim;
-      xt[idx] = (ca == ck) ? ((ia == ik ? 1.f : 0.f) - invn) : 0.f;
-    }
-    for (int idx = tid; idx < n * H; idx += NTHREADS) {
-      const int node = idx / H, col = idx - node * H;
-      int f = feat[node];
-      f = max(0, min(m.nfeat - 1, f));
-      hA[(size_t)node * ND * H + col] = m.embed[f * H + col];
-    }
-    __syncthreads();
     for (int b = 0; b < m.nblocks; ++b) {
       const bool last = (b == m.nblocks - 1);
-      const int kind = last ? KIND_LAST : (b == 0 ? KIND_FIRST : KIND_MID);
       const bool htan = b > 0;
+      const int ekind = last ? TT_LAST : (b == 0 ? TT_FIRST : TT_MID);
       pbeg();
-      node_pre(b, htan);
+      {
+        const int kind = htan ? TT_NODE : TT_NODE1;
+        NodePre p{*this, b, a.tabs.cnt[kind], last ? 3 : 4, kind};
+        run_phase(p);
+      }
+      if (is_epi) epi_bar();     // P_s / P_r / P_h / h_in of every node are in global memory
       pend(P_NODE_PRE);
-      edge_phase(b, kind, htan);
-      pbeg();
-      if (!last) node_post(b, htan);
+      {
+        EdgePh p{*this, b, a.tabs.cnt[ekind], 2 * m.L - 1, ekind, htan, 0.f, 0.f, 0.f};
+        run_phase(p);
+      }
+      if (is_epi) epi_bar();     // coordinate accumulators and aggregated messages complete
+      pend(P_EDGE);
+      if (!last) {
+        NodePost p{*this, b, a.tabs.cnt[TT_NODE], m.L + 1, TT_NODE, htan};
+        run_phase(p);
+      }
+      if (is_epi) {
+        epi_bar();
+        const float invnb = 1.f / (float)(n - 1);
+        for (int i = tid; i < D; i += TC_EPI) TCF(xs)[i] += TCF(xacc)[i] * invnb;
+        if (!last)
+          for (int i = tid; i < D * D; i += TC_EPI) TCF(xt)[i] += TCF(xtacc)[i] * invnb;
+        epi_bar();
+      }
       pend(P_NODE_POST);
-      const float invnb = 1.f / (float)(n - 1);
-      for (int i = tid; i < D; i += NTHREADS) xs[i] += xacc[i] * invnb;
-      if (!last)
-        for (int i = tid; i < D * D; i += NTHREADS) xt[i] += xtacc[i] * invnb;
-      __syncthreads();
     }
-    const float fs = m.final_scaling[0];
-    for (int i = tid; i < D; i += NTHREADS) fout[i] = (xs[i] - xs0[i] - mu[i % dim]) * fs;
-    if (tid == 0) {
-      const float invnb = 1.f / (float)(n - 1);
-      float s = 0.f;
-      for (int d = 0; d < D; ++d) s += xt[d * D + d] + dacc[d] * invnb;
-      fout[D] = fs * (s - (float)D);
+    if (is_epi) {
+      const float fs = m.final_scaling[0];
+      for (int i = tid; i < D; i += TC_EPI) fout[i] = (TCF(xs)[i] - TCF(xs0)[i] - TCF(mu)[i % dim]) * fs;
+      if (tid == 0) {
+        const float invnb = 1.f / (float)(n - 1);
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s += TCF(xt)[d * D + d] + TCF(dacc)[d] * invnb;
+        fout[D] = fs * (s - (float)D);
+      }
     }
     __syncthreads();
   }
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) ecnf_solve_tc_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(TC_NT, 1) ecnf_solve_tc_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ long long s_traj;
   __shared__ float s_ctl[8];
   EngineTC eng(a);
@@ -833,7 +978,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ecnf_solve_tc_kernel(const __grid
   eng.finish(reinterpret_cast<long long*>(reinterpret_cast<char*>(a.counter) + 64));
 }
 
-// ---- weight images: fp32 [K][N] (flax kernel) -> bf16 hi / lo in the canonical layout with rows = N ----------------
+// ---- weight images: fp32 [K][N] (flax kernel) -> bf16 hi | lo, 128 lanes (out features; zero rows beyond N), two
+// consecutive k per 32-bit word, 4 words per 16-byte chunk:  uint4 index = (part * K/8 + chunk) * 128 + lane -----------
 struct TcPrepItem {
   int src_off;   // floats, into the parameter buffer
   int dst_off;   // bytes, into the image buffer
@@ -846,51 +992,30 @@ struct TcPrepList {
 
 __global__ void tc_prep_kernel(const float* __restrict__ params, unsigned char* __restrict__ image, const TcPrepList list) {
   const TcPrepItem it = list.item[blockIdx.y];
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(image + it.dst_off);
-  __nv_bfloat16* lo = hi + it.K * it.N;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < it.K * it.N; idx += gridDim.x * blockDim.x) {
-    const int k = idx / it.N, nn = idx - k * it.N;
-    const float w = params[it.src_off + idx];
-    const __nv_bfloat16 h = __float2bfloat16(w);
-    const int d = canon_index(nn, k, it.N);
-    hi[d] = h;
-    lo[d] = __float2bfloat16(w - __bfloat162float(h));
+  uint32_t* dst = reinterpret_cast<uint32_t*>(image + it.dst_off);
+  const int words = it.K / 2;                 // per lane and part
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * words; idx += gridDim.x * blockDim.x) {
+    const int wd = idx / 128, lane = idx - wd * 128;
+    float x0 = 0.f, x1 = 0.f;
+    if (lane < it.N) {
+      x0 = params[it.src_off + (size_t)(2 * wd) * it.N + lane];
+      x1 = params[it.src_off + (size_t)(2 * wd + 1) * it.N + lane];
+    }
+    uint32_t h, l;
+    split_pack(x0, x1, h, l);
+    const size_t o = ((size_t)(wd >> 2) * 128 + lane) * 4 + (wd & 3);
+    dst[o] = h;
+    dst[(size_t)(it.K / 8) * 128 * 4 + o] = l;
   }
 }
 
-#undef stage
-#undef G
-#undef macc
-#undef vecs
-#undef xt
-#undef xtacc
-#undef dacc
-#undef xs
-#undef xs0
-#undef xacc
-#undef mu
-#undef tau
-#undef cvec
-#undef rowsd
-#undef rdot
-#undef gv
-#undef gs1
-#undef glen
-#undef ginv
-#undef ge
-#undef rowslot
-#undef rowgrp
-#undef gi
-#undef gj
-#undef giz
-#undef mbar_mma
-#undef mbar_w
-#undef tmem_slot
-#undef prof_s
-#undef hA
-#undef hB
-#undef Ps
-#undef Pr
-#undef Mg
+__global__ void tc_tables_kernel(uint32_t* __restrict__ out, int n, int dim, TcTabs tabs) {
+  const int k = threadIdx.x;
+  if (k < TT_COUNT) tc_pack(k, n, dim, out + (size_t)tabs.off[k] * TC_TILE_WORDS);
+}
+
+#undef TCF
+#undef TCI
+#undef TCW
 
 }  // namespace ecnf_solve_detail

@@ -57,6 +57,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier among `nthreads` threads (a multiple of 32) of the CTA; id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar` (size multiple of 16, 16-byte aligned)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -72,7 +79,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
          ((uint64_t)1 << 46);
 }
-// instruction descriptor for kind::f16, A = B = bf16 (K-major), D = fp32 (cute::UMMA::InstrDescriptor)
+// instruction descriptor for kind::f16, A = B = bf16 (K-major), D = fp32 (cute::UMMA::InstrDescriptor);
+// OR in IDESC_B_MN for a B operand stored MN-major (validated by tools/probe_tc2.cu)
+constexpr uint32_t IDESC_B_MN = 1u << 16;
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }

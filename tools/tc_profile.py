@@ -8,9 +8,9 @@ from ecnf_b200.cnf import build_cnf
 from ecnf_b200.engine import PackedParams
 from ecnf_b200.nets.egnn import init_flat_params
 
-NAMES = ["node_pre", "node_post", "meta", "build", "wait_mma", "epilogue", "messages", "sync+issue", "coords", "edge_init", "misc",
-         "  epi_ld", "  epi_act", "  epi_st", "  msg_dot", "  msg_stage", "  msg_loop", "  msg_seg", "  msg_flush", "  build_gather", "  build_act"]
-NTOP = 11
+NAMES = ["node_pre", "edge", "node_post", "  wait_mma(epi)", "  build", "  epilogue", "  messages", "  coords", "  weight_load", "  tile_meta",
+         "  issue_warp_wait", "misc"]
+NTOP = 3
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 cnf = build_cnf(13, 3, 0.01, 1.0, 3, (128, 128, 128), 64, 8, 1)
 eng = cnf.engine
