@@ -21,14 +21,14 @@ struct TcImages {
 
 // shared-memory carve-up of the tensor-core engine (byte offsets), computed on the host
 struct TcSmemLayout {
-  int bop, macc, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, colw, coloffS, coloffR, colsd, colmrow, pm, grpw, hdr,
+  int bop, macc, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, colw, coloffS, coloffR, colsd, colmrow, colijk, pm, grpw, hdr,
       pdot, wA, wB, cdbuf, egv, eglen, eginv, egs1, egiz, bars, prof, total_bytes;
   int mrows;   // rows of the message accumulator (a window of whole receivers)
 };
 
 // tile tables of the tensor-core engine: which (group, slot) row sits in which accumulator column (ecnf_solve_tc.cuh)
 enum { TT_NODE1 = 0, TT_NODE, TT_FIRST, TT_MID, TT_LAST, TT_COUNT };
-constexpr int TC_TILE_WORDS = 208;   // 128 column words + 64 group words + 16 header words
+constexpr int TC_TILE_WORDS = 240;   // 128 column + 64 group + 16 header + 16 primal-position + 4 mask words (+ pad)
 struct TcTabs {
   const uint32_t* base;
   int off[TT_COUNT];   // first tile of each kind

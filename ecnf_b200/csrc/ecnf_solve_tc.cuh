@@ -19,8 +19,9 @@
 //   * every Dense layer is 3 x (K/16) tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-17 relative per
 //     product, measured 4e-6 by tools/probe_tc2.cu) -- single-pass bf16/tf32 misses the 1e-4 tolerance on log q;
 //   * two tiles are in flight (two accumulators, two B buffers): while the epilogue threads work on one, the tensor
-//     core multiplies the other.  A dedicated warp issues the MMAs; hand-over is by mbarriers only
-//     (epilogue -> "ready[s]" -> MMA -> tcgen05.commit -> "done[s]" -> epilogue);
+//     core multiplies the other.  There is no CTA barrier in the layer chain: every thread counts itself in on a
+//     shared-memory arrival counter when its part of the next operand is written, the LAST one to arrive issues the
+//     MMAs, and tcgen05.commit -> mbarrier "done[s]" hands the accumulator back to the threads;
 //   * the only cross-lane work are the two Dense(1) heads (attention logit, coordinate head): a 62-shuffle transposing
 //     butterfly per warp + one 4-way sum through shared memory;
 //   * tile composition (which (group, slot) sits in which column) is precomputed per (n, dim, kind) into a table.
@@ -33,8 +34,8 @@ namespace ecnf_solve_detail {
 using namespace ecnf_tc;
 
 constexpr int TCU = 128, TCH = 64;
-constexpr int TC_NT = 288;          // 8 epilogue warps + 1 MMA-issue warp
-constexpr int TC_EPI = 256;
+constexpr int TC_NT = 256;          // 8 warps: thread (f, hh) owns feature / TMEM lane f and the column half hh
+constexpr int TC_EPI = TC_NT;
 constexpr int TC_BOP = 65536;       // one B-operand buffer: hi image [K = 128][N = 128] + lo image
 constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;
 constexpr int TC_WCOL = 256;        // first TMEM column of the weight buffers (accumulators: [0, 128) and [128, 256))
@@ -44,7 +45,7 @@ constexpr uint32_t CW_VALID = 1u << 31, CW_PRIMAL = 1u << 30, CW_DUP = 1u << 29;
 __host__ __device__ __forceinline__ int cw_gid(uint32_t w) { return (int)(w & 1023u); }
 __host__ __device__ __forceinline__ int cw_q(uint32_t w) { return (int)((w >> 10) & 255u); }
 __host__ __device__ __forceinline__ int cw_pc(uint32_t w) { return (int)((w >> 18) & 63u); }
-enum { TH_NC0 = 0, TH_NC1, TH_N, TH_G0, TH_NG, TH_WIN, TH_FLUSH, TH_IFIRST, TH_ILAST };
+enum { TH_NC0 = 0, TH_NC1, TH_N, TH_G0, TH_NG, TH_WIN, TH_FLUSH, TH_IFIRST, TH_ILAST, TH_SEGS };
 
 __host__ __device__ inline int tc_macc_rows(int n, int dim) {
   const int ND = 1 + n * dim;
@@ -53,7 +54,8 @@ __host__ __device__ inline int tc_macc_rows(int n, int dim) {
 }
 
 // Packs the groups (nodes or edges) of one table kind into tiles; returns the tile count, writes them when out != null.
-// Tile = 128 column words | 64 group words (slot split + first columns of the group's segments) | 16 header words.
+// Tile = 128 column words | 64 group words (slot split + first columns of the group's segments) | 16 header words |
+// (16 unused) | 4 primal masks.  Padding columns between segments are invalid (word 0).
 __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) {
   const int D = n * dim, ND = 1 + D;
   const bool edge = kind >= TT_FIRST;
@@ -61,6 +63,8 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
   const int r = kind == TT_NODE1 ? 1 : kind == TT_NODE ? ND : kind == TT_FIRST ? 1 + 2 * dim : kind == TT_MID ? ND : 1 + dim;
   // message-accumulator window: tiles of the message-passing kinds never span two windows of receivers
   const int window = (kind == TT_FIRST || kind == TT_MID) ? (tc_macc_rows(n, dim) / ND) * (n - 1) : 0;
+  // segments start on 8-column chunk boundaries (the activation rule works chunk-wise); all-primal node tiles pack densely
+  const int al = kind == TT_NODE1 ? 1 : 8;
   int tile = 0, used0 = 0, used1 = 0, half = 0, ng = 0, g0 = 0;
   auto tp = [&](int t) { return out + (size_t)t * TC_TILE_WORDS; };
   auto close = [&](int gnext, int flush) {
@@ -78,6 +82,15 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
       h[TH_FLUSH] = (uint32_t)flush;
       h[TH_IFIRST] = (uint32_t)(edge ? g0 / (n - 1) : g0);
       h[TH_ILAST] = (uint32_t)(edge ? (g0 + ng - 1) / (n - 1) : g0 + ng - 1);
+      // primal masks (4 x 32 columns) and, per half, which 8-column chunks start a segment
+      uint32_t* t = tp(tile);
+      uint32_t segs = 0u;
+      for (int c = 0; c < 128; ++c)
+        if (t[c] & CW_PRIMAL) {
+          t[224 + (c >> 5)] |= 1u << (c & 31);
+          if ((c & 7) == 0) segs |= 1u << (c >> 3);
+        }
+      h[TH_SEGS] = segs;
     }
     ++tile;
     used0 = used1 = 0; half = 0; ng = 0; g0 = gnext;
@@ -97,6 +110,7 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
       if (ng == 0 && used0 == 0 && out)
         for (int k = 0; k < TC_TILE_WORDS; ++k) tp(tile)[k] = 0;
       if (half == 0) {
+        used0 = (used0 + al - 1) / al * al;
         const int rem = 64 - used0;
         if (r <= rem) {
           seg(g, used0, 0, r, false);
@@ -115,6 +129,7 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
         if (r > 64) { close(g, 0); }
         continue;
       }
+      used1 = (used1 + al - 1) / al * al;
       const int rem = 64 - used1;
       if (r <= rem) {
         seg(g, 64 + used1, 0, r, false);
@@ -137,7 +152,7 @@ __host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim) {
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
   L.bop = take(2 * TC_BOP);
   L.mrows = tc_macc_rows(n, dim);
-  L.macc = take(2 * L.mrows * TCU * 4);    // aggregated messages of the receiver window, one copy per column half
+  L.macc = take(2 * (L.mrows + 1) * TCU * 4);   // aggregated messages of the receiver window, one copy per column half (+ a dump row)
   L.xt = take(D * D * 4);
   L.xtacc = take(D * D * 4);
   L.dacc = take(D * 4);
@@ -154,6 +169,7 @@ __host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim) {
   L.coloffR = take(2 * 128 * 4);
   L.colsd = take(2 * 128 * 4);
   L.colmrow = take(2 * 128 * 4);
+  L.colijk = take(2 * 128 * 4);
   L.pm = take(2 * 4 * 4);
   L.grpw = take(2 * 64 * 4);
   L.hdr = take(2 * 16 * 4);
@@ -188,19 +204,19 @@ struct EngineTC {
   const TcImages& img;
   const int n, dim, D, ND, E;
   const int tid, f, hh, warp, lane;
-  const bool is_epi;
   uint32_t tmem;         // TMEM base address
   uint32_t lane_addr;    // (32 * (warp & 3)) << 16
-  uint32_t ph0, ph1;     // phase counters of the two slots (ready[] for the issue warp, done[] for the epilogue threads)
+  uint32_t ph0, ph1;     // completed-phase counters of done[0], done[1]
 
-  enum { P_NODE_PRE, P_EDGE, P_NODE_POST, P_WAIT, P_BUILD, P_EPI, P_MSG, P_COORD, P_WLOAD, P_META, P_CTRL_WAIT, P_MISC, P_NCOUNT };
+  enum { P_NODE_PRE, P_EDGE, P_NODE_POST, P_WAIT, P_BUILD, P_EPI, P_MSG, P_COORD, P_WLOAD, P_META, P_CTRL_WAIT, P_MISC,
+         P_EPI_LD, P_EPI_ACT, P_EPI_ST, P_ARRIVE, P_GATHER, P_NCOUNT };
 #ifdef ECNF_TC_PROFILE
   long long prof_t0, prof_t1;
   __device__ __forceinline__ long long* prof_s() const { return reinterpret_cast<long long*>(smem_tc + a.lay.prof); }
   __device__ __forceinline__ void pbeg() { prof_t0 = clock64(); }
   __device__ __forceinline__ void pend(int k) { const long long t1 = clock64(); if (tid == 0) prof_s()[k] += t1 - prof_t0; prof_t0 = t1; }
   __device__ __forceinline__ void qbeg() { prof_t1 = clock64(); }
-  __device__ __forceinline__ void qend(int k) { const long long t1 = clock64(); if (tid == 0 || tid == TC_EPI) prof_s()[k] += t1 - prof_t1; prof_t1 = t1; }
+  __device__ __forceinline__ void qend(int k) { const long long t1 = clock64(); if (tid == 0) prof_s()[k] += t1 - prof_t1; prof_t1 = t1; }
 #else
   __device__ __forceinline__ void pbeg() {}
   __device__ __forceinline__ void pend(int) {}
@@ -210,10 +226,10 @@ struct EngineTC {
 
   __device__ __forceinline__ float* ode_ptr() const { return TCF(ode); }
   __device__ __forceinline__ float* red_ptr() const { return TCF(red); }
-  __device__ __forceinline__ uint64_t* bar_ready(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + s; }
+  __device__ __forceinline__ uint32_t* arrivals(int s) const { return reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars) + s; }
   __device__ __forceinline__ uint64_t* bar_done(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + 2 + s; }
   __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars + 32); }
-  // per-CTA global scratch (L2 resident): h, h_in [n][ND][H]; P_s, P_r, P_h, aggregated messages [n][ND][U]
+  // per-CTA global scratch (L2 resident): h, h_in [n][ND][H]; P_s, P_r, aggregated messages, P_h [n][ND][U]
   __device__ __forceinline__ float* hA() const { return a.scratch + (size_t)blockIdx.x * a.scratch_stride; }
   __device__ __forceinline__ float* hB() const { return hA() + (size_t)n * ND * H; }
   __device__ __forceinline__ float* Ps() const { return hB() + (size_t)n * ND * H; }
@@ -224,9 +240,9 @@ struct EngineTC {
   __device__ __forceinline__ EngineTC(const KernelArgs& a_)
       : a(a_), m(a_.m), img(a_.img), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim), ND(1 + a_.m.n * a_.m.dim),
         E(a_.m.n * (a_.m.n - 1)), tid(threadIdx.x), f(threadIdx.x & 127), hh((threadIdx.x >> 7) & 1), warp(threadIdx.x >> 5),
-        lane(threadIdx.x & 31), is_epi(threadIdx.x < TC_EPI) {
+        lane(threadIdx.x & 31) {
     if (tid == 0) {
-      mbar_init(bar_ready(0), TC_EPI); mbar_init(bar_ready(1), TC_EPI);
+      *arrivals(0) = 0u; *arrivals(1) = 0u;
       mbar_init(bar_done(0), 1); mbar_init(bar_done(1), 1);
 #ifdef ECNF_TC_PROFILE
       for (int k = 0; k < P_NCOUNT; ++k) prof_s()[k] = 0;
@@ -240,7 +256,7 @@ struct EngineTC {
     tmem = *tmem_slot();
     lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     ph0 = ph1 = 0;
-    if (is_epi) {   // accumulators start finite (columns beyond a tile's N are read but never used)
+    {   // accumulators start finite (columns beyond a tile's N are read but never used)
       uint32_t z[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) z[c] = 0u;
@@ -262,51 +278,57 @@ struct EngineTC {
     if (warp == 0) tmem_dealloc(tmem, 512);
   }
 
-  // ---- hand-over between the epilogue threads and the MMA-issue warp ----------------------------------------------
-  __device__ __forceinline__ void epi_bar() const { named_bar_sync(1, TC_EPI); }
-  // epilogue: my part of slot s's next operands (B in shared memory, weights / drained accumulator in TMEM) is complete
-  __device__ __forceinline__ void arrive_ready(int s) {
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(bar_ready(s));
-  }
-  __device__ __forceinline__ void wait_slot(uint64_t* bar0, uint64_t* bar1, int s) {
-    if (s == 0) { mbar_wait(bar0, ph0 & 1); ph0++; }
-    else { mbar_wait(bar1, ph1 & 1); ph1++; }
+  // ---- hand-over between the threads and the tensor core ------------------------------------------------------------
+  __device__ __forceinline__ void epi_bar() const { __syncthreads(); }
+  __device__ __forceinline__ void wait_done(int s) {
+    qbeg();
+    const uint32_t par = (s ? ph1 : ph0) & 1u;
+    mbar_wait(bar_done(s), par);
+    ph0 += (s == 0); ph1 += (s != 0);
     tc_fence_after();
+    qend(P_WAIT);
   }
-  __device__ __forceinline__ void wait_done(int s) { qbeg(); wait_slot(bar_done(0), bar_done(1), s); qend(P_WAIT); }
-  __device__ __forceinline__ void ctrl_wait_ready(int s) { qbeg(); wait_slot(bar_ready(0), bar_ready(1), s); qend(P_CTRL_WAIT); }
-
-  // issue warp: acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s] (K x N), 3-pass split; commit -> done[s]
+  // acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s] (K x N), 3-pass split; commit -> done[s].  One thread.
   __device__ __forceinline__ void issue_mma(int s, uint32_t a_col, int K, int N) {
-    __syncwarp();
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_B_MN;
-      const uint32_t bsm = smem_u32(smem_tc + a.lay.bop) + (uint32_t)s * TC_BOP;
-      uint64_t bh = make_sdesc(bsm, TC_LBO, TC_SBO);
-      uint64_t bl = make_sdesc(bsm + 32768u, TC_LBO, TC_SBO);
-      const uint32_t acc = tmem + 128u * s;
-      uint32_t a_hi = tmem + a_col, a_lo = tmem + a_col + (uint32_t)(K >> 1);
-      const int nk = K >> 4;
-      mma_ts(acc, a_hi, bh, idesc, 0u);
+    const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_B_MN;
+    const uint32_t bsm = smem_u32(smem_tc + a.lay.bop) + (uint32_t)s * TC_BOP;
+    uint64_t bh = make_sdesc(bsm, TC_LBO, TC_SBO);
+    uint64_t bl = make_sdesc(bsm + 32768u, TC_LBO, TC_SBO);
+    const uint32_t acc = tmem + 128u * s;
+    uint32_t a_hi = tmem + a_col, a_lo = tmem + a_col + (uint32_t)(K >> 1);
+    const int nk = K >> 4;
+    mma_ts(acc, a_hi, bh, idesc, 0u);
+    mma_ts(acc, a_lo, bh, idesc, 1u);
+    mma_ts(acc, a_hi, bl, idesc, 1u);
+    for (int ks = 1; ks < nk; ++ks) {
+      bh += (2u * TC_LBO) >> 4; bl += (2u * TC_LBO) >> 4; a_hi += 8; a_lo += 8;
+      mma_ts(acc, a_hi, bh, idesc, 1u);
       mma_ts(acc, a_lo, bh, idesc, 1u);
       mma_ts(acc, a_hi, bl, idesc, 1u);
-      for (int ks = 1; ks < nk; ++ks) {
-        bh += (2u * TC_LBO) >> 4; bl += (2u * TC_LBO) >> 4; a_hi += 8; a_lo += 8;
-        mma_ts(acc, a_hi, bh, idesc, 1u);
-        mma_ts(acc, a_lo, bh, idesc, 1u);
-        mma_ts(acc, a_hi, bl, idesc, 1u);
-      }
-      mma_commit(bar_done(s));
     }
-    __syncwarp();
+    mma_commit(bar_done(s));
+  }
+  // My part of slot s's next operands (B in shared memory, weights / drained accumulator in TMEM) is complete.  The
+  // arrival counter is an acq_rel read-modify-write chain: the thread that completes the count of TC_NT has every
+  // other thread's writes ordered before it and issues the layer.
+  __device__ __forceinline__ void hand_over(int s, uint32_t a_col, int K) {
+    qbeg();
+    fence_proxy_async();
+    tc_fence_before();
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(arrivals(s))) : "memory");
+    if ((old & (TC_NT - 1)) == TC_NT - 1) {
+      tc_fence_after();
+      issue_mma(s, a_col, K, hdr(s, TH_N));
+    }
+    qend(P_ARRIVE);
   }
 
   // ---- per-thread column helpers (thread (f, hh): feature f, columns [64 hh, +64) of slot s) -----------------------
+  __device__ __forceinline__ uint32_t my_acc(int s) const { return tmem + 128u * s + lane_addr + 64u * hh; }
   __device__ __forceinline__ void ld_acc(int s, float (&v)[64]) {
     uint32_t x[32], y[32];
-    const uint32_t addr = tmem + 128u * s + lane_addr + 64u * hh;
+    const uint32_t addr = my_acc(s);
     tmem_ld32(addr, x);
     tmem_ld32(addr + 32u, y);
     tmem_wait_ld();
@@ -325,21 +347,24 @@ struct EngineTC {
       *reinterpret_cast<uint4*>(base + 32768 + g8 * (int)TC_SBO) = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
-  // bias + SiLU on primal columns, silu'(z_primal) * z on the tangent columns that follow them
+  // Activation rule: a = silu(z + bias) on primal columns, a-dot = silu'(z_primal) z-dot on the tangent columns that
+  // follow them.  Segments start on 8-column chunk boundaries, so the primal column of a segment is column 0 of a chunk
+  // (a static register) and silu' is a running per-thread scalar; `segs` = which of my 8 chunks start a segment.
   __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int s) {
-    const uint32_t m0 = TCW(pm)[s * 4 + 2 * hh], m1 = TCW(pm)[s * 4 + 2 * hh + 1];
+    const uint32_t segs = (TCW(hdr)[s * 16 + TH_SEGS] >> (8 * hh)) & 0xffu;
     float cur = 0.f;
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-      if (pr) {
-        const float z = v[c] + bias;
+    for (int ch = 0; ch < 8; ++ch) {
+      if ((segs >> ch) & 1u) {
+        const float z = v[8 * ch] + bias;
         const float sg = __fdividef(1.f, 1.f + __expf(-z));
         cur = sg * (1.f + z * (1.f - sg));
-        v[c] = z * sg;
+        v[8 * ch] = z * sg;
       } else {
-        v[c] *= cur;
+        v[8 * ch] *= cur;
       }
+#pragma unroll
+      for (int u = 1; u < 8; ++u) v[8 * ch + u] *= cur;
     }
   }
   template <int W>   // 2W partial sums -> W, exchanging with lane ^ (W/2)
@@ -370,12 +395,11 @@ struct EngineTC {
     bfly_round<2>(x);
     *reinterpret_cast<float2*>(pd + 2 * lane) = make_float2(x[0], x[1]);
   }
-  // weight image (hi | lo, K x 128 lanes) -> TMEM columns [col, col + K)
+  // weight image (hi | lo, K x 128 lanes) -> registers -> TMEM columns [col, col + K)
   template <int K>
-  __device__ __forceinline__ void load_w(int img_off, uint32_t col) {
+  __device__ __forceinline__ void fetch_w(int img_off, uint32_t (&wv)[2][K / 4]) {
     constexpr int NC = K / 16;     // uint4 chunks per thread and part
     const uint4* src = reinterpret_cast<const uint4*>(img.base + img_off);
-    uint32_t wv[2][NC * 4];
 #pragma unroll
     for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -383,6 +407,9 @@ struct EngineTC {
         const uint4 q = __ldg(src + (size_t)(p * (K / 8) + hh * NC + j) * 128 + f);
         wv[p][4 * j] = q.x; wv[p][4 * j + 1] = q.y; wv[p][4 * j + 2] = q.z; wv[p][4 * j + 3] = q.w;
       }
+  }
+  template <int K>
+  __device__ __forceinline__ void store_w(const uint32_t (&wv)[2][K / 4], uint32_t col) {
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       const uint32_t addr = tmem + col + lane_addr + (uint32_t)(p * (K / 2) + hh * (K / 4));
@@ -391,13 +418,27 @@ struct EngineTC {
     }
     tmem_wait_st();
   }
+  template <int K>
+  __device__ __forceinline__ void load_w(int img_off, uint32_t col) {
+    uint32_t wv[2][K / 4];
+    fetch_w<K>(img_off, wv);
+    store_w<K>(wv, col);
+  }
 
   // ---- tile tables ---------------------------------------------------------------------------------------------------
   __device__ __forceinline__ const uint32_t* tile_ptr(int kind, int tile) const {
     return a.tabs.base + (size_t)(a.tabs.off[kind] + tile) * TC_TILE_WORDS;
   }
-  __device__ __forceinline__ int tile_N(int kind, int tile) const { return (int)__ldg(tile_ptr(kind, tile) + 192 + TH_N); }
   __device__ __forceinline__ int hdr(int s, int k) const { return TCI(hdr)[s * 16 + k]; }
+  // threads 128..227 copy the tile's group words, header, primal-column positions and primal masks
+  __device__ __forceinline__ void meta_copy(int s, const uint32_t* tp) {
+    if (tid >= 128 && tid < 228) {
+      const uint32_t w = __ldg(tp + tid);
+      if (tid < 192) TCW(grpw)[s * 64 + (tid - 128)] = w;
+      else if (tid < 208) TCW(hdr)[s * 16 + (tid - 192)] = w;
+      else if (tid >= 224) TCW(pm)[s * 4 + (tid - 224)] = w;
+    }
+  }
 
   // =============================================================================================================
   // The software pipeline shared by the three phases.  P provides
@@ -405,7 +446,7 @@ struct EngineTC {
   //   prologue()                  epilogue threads, before the first tile
   //   build(s, tile)              epilogue threads: first B operand of the tile
   //   epi(s, tile, w)             epilogue threads: consume the accumulator of layer w (and write the next B operand)
-  //   wload(w, col)               epilogue threads: weights of layer w -> TMEM columns col (stream only)
+  //   wimg(w)                     image offset of the weights of layer w (stream only)
   //   a_col(q, w), K(w)           MMA operand position / depth for layer w at stream position q
   // =============================================================================================================
   template <class P>
@@ -413,38 +454,38 @@ struct EngineTC {
     const int ntiles = p.ntiles, NL = p.NL;
     const int npairs = (ntiles + 1) >> 1;
     const int total_q = npairs * NL;
-    if (is_epi) {
-      p.prologue();
-      if (p.stream) {
-        p.wload(0, TC_WCOL);
-        if (total_q > 1) p.wload(1 % NL, TC_WCOL + 128);
-      }
+    p.prologue();
+    if (p.stream) {
+      load_w<TCU>(p.wimg(0), TC_WCOL);
+      if (total_q > 1) load_w<TCU>(p.wimg(1 % NL), TC_WCOL + 128);
     }
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < 2; ++s) {
       if (s >= ntiles) continue;
-      if (is_epi) { p.build(s, s); arrive_ready(s); }
-      else { ctrl_wait_ready(s); issue_mma(s, p.a_col(0, 0), p.K(0), tile_N(p.kind, s)); }
+      p.build(s, s);
+      hand_over(s, p.a_col(0, 0), p.K(0));
     }
     int q = 0;
+#pragma unroll 1
     for (int pr = 0; pr < npairs; ++pr) {
+#pragma unroll 1
       for (int w = 0; w < NL; ++w, ++q) {
-#pragma unroll
+#pragma unroll 1
         for (int s = 0; s < 2; ++s) {
           const int tile = 2 * pr + s;
           if (tile >= ntiles) continue;
           const bool last_slot = (s == 1) || (tile + 1 >= ntiles);
           const int ntile = tile + 2;
-          if (is_epi) {
-            wait_done(s);
-            if (p.stream && last_slot && q + 2 < total_q) { qbeg(); p.wload((w + 2) % NL, TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
-            p.epi(s, tile, w);
-            if (w < NL - 1) arrive_ready(s);
-            else if (ntile < ntiles) { p.build(s, ntile); arrive_ready(s); }
-          } else {
-            if (w < NL - 1) { ctrl_wait_ready(s); issue_mma(s, p.a_col(q + 1, w + 1), p.K(w + 1), tile_N(p.kind, tile)); }
-            else if (ntile < ntiles) { ctrl_wait_ready(s); issue_mma(s, p.a_col(q + 1, 0), p.K(0), tile_N(p.kind, ntile)); }
-          }
+          // the weights two layers ahead go into the buffer that layer q's MMAs (complete once done[last slot]
+          // fires) have been reading: fetch them into registers before the wait, store after it
+          const bool do_w = p.stream && last_slot && q + 2 < total_q;
+          uint32_t wv[2][TCU / 4];
+          if (do_w) fetch_w<TCU>(p.wimg((w + 2) % NL), wv);
+          wait_done(s);
+          if (do_w) { qbeg(); store_w<TCU>(wv, TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
+          p.epi(s, tile, w);
+          if (w < NL - 1) hand_over(s, p.a_col(q + 1, w + 1), p.K(w + 1));
+          else if (ntile < ntiles) { p.build(s, ntile); hand_over(s, p.a_col(q + 1, 0), p.K(0)); }
         }
       }
     }
@@ -459,11 +500,8 @@ struct EngineTC {
       const uint32_t w = __ldg(tp + tid);
       TCW(colw)[s * 128 + tid] = w;
       TCI(coloffR)[s * 128 + tid] = (w & CW_VALID) ? cw_gid(w) * ND + cw_q(w) : -1;
-      const uint32_t bal = __ballot_sync(0xffffffffu, (w & CW_PRIMAL) != 0u);
-      if (lane == 0) TCW(pm)[s * 4 + warp] = bal;
-    } else if (tid < 144) {
-      TCW(hdr)[s * 16 + (tid - 128)] = __ldg(tp + 192 + (tid - 128));
     }
+    meta_copy(s, tp);
     epi_bar();
     qend(P_META);
   }
@@ -477,7 +515,7 @@ struct EngineTC {
     static constexpr bool stream = false;
     __device__ __forceinline__ uint32_t a_col(int, int w) const { return TC_WCOL + 64u * w; }
     __device__ __forceinline__ int K(int) const { return TCH; }
-    __device__ __forceinline__ void wload(int, uint32_t) {}
+    __device__ __forceinline__ int wimg(int) const { return 0; }
     __device__ __forceinline__ void prologue() {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
@@ -496,11 +534,13 @@ struct EngineTC {
       const KernelArgs& a = e.a;
       e.node_meta(s, kind, tile);
       float v[64];
-      const float* src = e.hA();
+      const float* src = e.hA() + e.f;
+      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
-        v[c] = (ro >= 0 && e.f < TCH) ? src[(size_t)ro * TCH + e.f] : 0.f;
+        const int ro = ro_[c];
+        const float x = src[(size_t)(ro >= 0 && e.f < TCH ? ro : 0) * TCH];
+        v[c] = (ro >= 0 && e.f < TCH) ? x : 0.f;
       }
       if (e.f < TCH) e.write_B(s, v);
     }
@@ -508,31 +548,22 @@ struct EngineTC {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       float v[64];
+      const float cv = TCF(cvec)[e.f & (TCH - 1)];
+      const float bias = w == 0 ? cv : (w == 1 ? 0.f : (w == 2 ? bp.be[0][e.f] : bp.bh[0][e.f]));
       e.ld_acc(s, v);
       const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
-      if (w == 0) {
-        if (e.f < TCH) {
-          const float cv = TCF(cvec)[e.f];
-          float* dst = e.hB();
+      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
+      const bool act = (w > 0) || (e.f < TCH);
+      const int ld = w == 0 ? TCH : TCU;
+      float* dst = (w == 0 ? e.hB() : w == 1 ? e.Ps() : w == 2 ? e.Pr() : e.Ph()) + e.f;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-            if (pr) v[c] += cv;
-            const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
-            if (ro >= 0) dst[(size_t)ro * TCH + e.f] = v[c];    // a repeated primal column rewrites the same value
-          }
-          e.write_B(s, v);
-        }
-      } else {
-        const float bias = w == 1 ? 0.f : (w == 2 ? bp.be[0][e.f] : bp.bh[0][e.f]);
-        float* dst = w == 1 ? e.Ps() : (w == 2 ? e.Pr() : e.Ph());
-#pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-          const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
-          if (ro >= 0) dst[(size_t)ro * TCU + e.f] = pr ? v[c] + bias : v[c];
-        }
+      for (int c = 0; c < 64; ++c) {
+        const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+        v[c] += pr ? bias : 0.f;
+        const int ro = ro_[c];
+        if (ro >= 0 && act) dst[(size_t)ro * ld] = v[c];    // a repeated primal column rewrites the same value
       }
+      if (w == 0 && e.f < TCH) e.write_B(s, v);
     }
   };
 
@@ -547,21 +578,22 @@ struct EngineTC {
     __device__ __forceinline__ uint32_t a_col(int q, int) const { return TC_WCOL + 128u * (q & 1); }
     __device__ __forceinline__ int K(int) const { return TCU; }
     __device__ __forceinline__ void prologue() {}
-    __device__ __forceinline__ void wload(int w, uint32_t col) {
+    __device__ __forceinline__ int wimg(int w) const {
       const TcImgBlock& ib = e.img.blk[b];
       const int L = e.m.L;
-      e.template load_w<TCU>(w == 0 ? ib.Wh0m : (w < L ? ib.Wh[w] : ib.WhL), col);
+      return w == 0 ? ib.Wh0m : (w < L ? ib.Wh[w] : ib.WhL);
     }
     __device__ __forceinline__ void build(int s, int tile) {
       const KernelArgs& a = e.a;
       e.node_meta(s, kind, tile);
       float v[64];
-      const float* src = e.Mg();
+      const float* src = e.Mg() + e.f;
+      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
-        v[c] = src[(size_t)(ro >= 0 ? ro : 0) * TCU + e.f];
-        if (ro < 0) v[c] = 0.f;
+        const int ro = ro_[c];
+        const float x = src[(size_t)(ro >= 0 ? ro : 0) * TCU];
+        v[c] = ro >= 0 ? x : 0.f;
       }
       e.write_B(s, v);
     }
@@ -569,23 +601,28 @@ struct EngineTC {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int L = e.m.L;
+      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
       float v[64];
       if (w == 0) {
-        // issue the P_h loads before the accumulator arrives in registers
         const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
-        const float* ph = e.Ph();
-        float pv[64];
-#pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-          const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
-          const bool use = ro >= 0 && (pr || htan);
-          pv[c] = ph[(size_t)(use ? ro : 0) * TCU + e.f];
-          if (!use) pv[c] = 0.f;
-        }
+        const float* ph = e.Ph() + e.f;
+        // + P_h (primal always; tangent columns where h_in carries tangents)
         e.ld_acc(s, v);
 #pragma unroll
-        for (int c = 0; c < 64; ++c) v[c] += pv[c];
+        for (int cb = 0; cb < 64; cb += 16) {
+          float pv[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int c = cb + u;
+            const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+            const int ro = ro_[c];
+            const bool use = ro >= 0 && (pr || htan);
+            const float x = ph[(size_t)(use ? ro : 0) * TCU];
+            pv[u] = use ? x : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[cb + u] += pv[u];
+        }
         e.act_rule(v, 0.f, s);
         e.write_B(s, v);
       } else if (w < L) {
@@ -594,21 +631,28 @@ struct EngineTC {
         e.act_rule(v, bias, s);
         e.write_B(s, v);
       } else {
+        const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
+        const float bias = bp.bh[L][e.f & (TCH - 1)];
+        const float* hin = e.hB() + (e.f & (TCH - 1));
+        float* dst = e.hA() + e.f;
         e.ld_acc(s, v);
         if (e.f < TCH) {
-          const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
-          const float bias = bp.bh[L][e.f];
-          const float* hin = e.hB();
-          float* dst = e.hA();
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-            const int ro = TCI(coloffR)[s * 128 + 64 * e.hh + c];
-            if (ro >= 0) {
-              float x = v[c];
-              if (pr) x += bias;
-              if (pr || htan) x += hin[(size_t)ro * TCH + e.f];
-              dst[(size_t)ro * TCH + e.f] = x;
+          for (int cb = 0; cb < 64; cb += 16) {
+            float hv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int c = cb + u;
+              const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+              const int ro = ro_[c];
+              const bool use = ro >= 0 && (pr || htan);
+              const float x = hin[(size_t)(use ? ro : 0) * TCH];
+              hv[u] = (use ? x : 0.f) + (pr ? bias : 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int ro = ro_[cb + u];
+              if (ro >= 0) dst[(size_t)ro * TCH] = v[cb + u] + hv[u];
             }
           }
         }
@@ -628,10 +672,10 @@ struct EngineTC {
     __device__ __forceinline__ uint32_t a_col(int q, int) const { return TC_WCOL + 128u * (q & 1); }
     __device__ __forceinline__ int K(int) const { return TCU; }
     __device__ __forceinline__ int ekind() const { return kind == TT_FIRST ? KIND_FIRST : kind == TT_MID ? KIND_MID : KIND_LAST; }
-    __device__ __forceinline__ void wload(int w, uint32_t col) {
+    __device__ __forceinline__ int wimg(int w) const {
       const TcImgBlock& ib = e.img.blk[b];
       const int L = e.m.L;
-      e.template load_w<TCU>(w < L - 1 ? ib.We[w + 1] : ib.Wx[w - (L - 1)], col);
+      return w < L - 1 ? ib.We[w + 1] : ib.Wx[w - (L - 1)];
     }
     __device__ __forceinline__ void prologue() {
       const KernelArgs& a = e.a;
@@ -643,7 +687,7 @@ struct EngineTC {
       for (int i = e.tid; i < D; i += TC_EPI) { TCF(xacc)[i] = 0.f; TCF(dacc)[i] = 0.f; }
       if (kind != TT_LAST) {
         for (int i = e.tid; i < D * D; i += TC_EPI) TCF(xtacc)[i] = 0.f;
-        for (int i = e.tid; i < 2 * a.lay.mrows * TCU; i += TC_EPI) TCF(macc)[i] = 0.f;
+        for (int i = e.tid; i < 2 * (a.lay.mrows + 1) * TCU; i += TC_EPI) TCF(macc)[i] = 0.f;
       }
       // per-edge geometry (egnn.py:73-76, numerical.py:7-10)
       for (int ed = e.tid; ed < e.E; ed += TC_EPI) {
@@ -672,17 +716,17 @@ struct EngineTC {
       if (e.tid < 128) {
         const uint32_t w = __ldg(tp + e.tid);
         const int win = (int)__ldg(tp + 192 + TH_WIN);
-        int oS = -1, oR = 0, mr = -1;
+        int oS = -1, oR = 0, mr = a.lay.mrows * TCU, ijk = 0;
         float sd = 0.f;
         if (w & CW_VALID) {
           const int ed = cw_gid(w), q = cw_q(w);
           const int i = ed / (n - 1), jj = ed - i * (n - 1);
           int j = i + 1 + jj; if (j >= n) j -= n;
-          int slot = 0;
+          int slot = 0, k = 0;
           if (q == 0) {
             sd = TCF(egs1)[ed];
           } else {
-            const int k = dirmap(ekind(), q - 1, i, j, dim);
+            k = dirmap(ekind(), q - 1, i, j, dim);
             slot = 1 + k;
             float acc = 0.f;
             for (int c = 0; c < dim; ++c)
@@ -690,20 +734,17 @@ struct EngineTC {
             sd = TCI(egiz)[ed] ? 0.f : 2.f * acc;
           }
           if (q == 0 || htan) { oS = (j * ND + slot) * TCU; oR = (i * ND + slot) * TCU; }
-          if (!(w & CW_DUP)) mr = ((i - win) * ND + slot) * TCU;
+          if (!(w & CW_DUP) && kind != TT_LAST) mr = ((i - win) * ND + slot) * TCU;
+          ijk = i | (j << 5) | (k << 10);
         }
         TCW(colw)[s * 128 + e.tid] = w;
         TCI(coloffS)[s * 128 + e.tid] = oS;
         TCI(coloffR)[s * 128 + e.tid] = oR;
         TCF(colsd)[s * 128 + e.tid] = sd;
         TCI(colmrow)[s * 128 + e.tid] = mr;
-        const uint32_t bal = __ballot_sync(0xffffffffu, (w & CW_PRIMAL) != 0u);
-        if (e.lane == 0) TCW(pm)[s * 4 + e.warp] = bal;
-      } else if (e.tid < 192) {
-        TCW(grpw)[s * 64 + (e.tid - 128)] = __ldg(tp + e.tid);
-      } else if (e.tid < 208) {
-        TCW(hdr)[s * 16 + (e.tid - 192)] = __ldg(tp + e.tid);
+        TCI(colijk)[s * 128 + e.tid] = ijk;
       }
+      e.meta_copy(s, tp);
       e.epi_bar();
       e.qend(P_META);
     }
@@ -733,6 +774,7 @@ struct EngineTC {
           v[cb + u] = os[u] >= 0 ? fmaf(sd, wdf, pa[u] + pb[u]) : sd * wdf;
         }
       }
+      e.qend(P_GATHER);
       e.act_rule(v, 0.f, s);
       e.write_B(s, v);
       e.qend(P_BUILD);
@@ -745,10 +787,12 @@ struct EngineTC {
       float v[64];
       e.qbeg();
       e.ld_acc(s, v);
+      e.qend(P_EPI_LD);
       e.act_rule(v, bias, s);
+      e.qend(P_EPI_ACT);
       if (w < NL - 1) {
         e.write_B(s, v);
-        e.qend(P_EPI);
+        e.qend(P_EPI_ST);
         if (w == L - 2 && kind != TT_LAST) messages(s, v);
         e.qend(P_MSG);
       } else {
@@ -785,20 +829,23 @@ struct EngineTC {
       }
       __syncwarp();
       {
-        // msg = m e,  msg-dot = m-dot e + m e (1 - e) (m-dot . wa)   accumulated per (receiver, slot) row
-        float* mac = TCF(macc) + (size_t)hh * a.lay.mrows * TCU + e.f;
+        // msg = m e,  msg-dot = m-dot e + m e (1 - e) (m-dot . wa)   accumulated per (receiver, slot) row; columns
+        // that do not contribute (repeated primal, padding) go to the dump row
+        float* mac = TCF(macc) + (size_t)hh * (a.lay.mrows + 1) * TCU + e.f;
         const float* wa_ = TCF(wA) + warp * 64;
         const float* wb_ = TCF(wB) + warp * 64;
-        const uint32_t m0 = TCW(pm)[s * 4 + 2 * hh], m1 = TCW(pm)[s * 4 + 2 * hh + 1];
-        float curm = 0.f;
+        const int* mr_ = TCI(colmrow) + s * 128 + 64 * hh;
+        const uint32_t segs = (TCW(hdr)[s * 16 + TH_SEGS] >> (8 * hh)) & 0xffu;
+        float curm = 0.f, eg = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-          if (pr) curm = v[c];
-          const int mr = TCI(colmrow)[s * 128 + 64 * hh + c];
-          if (mr >= 0) {
-            const float x = fmaf(curm, wb_[c], v[c] * wa_[c]);
-            mac[mr] += x;
+        for (int ch = 0; ch < 8; ++ch) {
+          const bool st = ((segs >> ch) & 1u) != 0u;     // a new edge starts here: its primal message and gate
+          curm = st ? v[8 * ch] : curm;
+          eg = st ? wa_[8 * ch] : eg;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = 8 * ch + u;
+            mac[mr_[c]] += fmaf(curm, wb_[c], v[c] * eg);
           }
         }
       }
@@ -810,7 +857,7 @@ struct EngineTC {
         const int rows = nrecv * e.ND;
         const float inv_sqrt_nb = rsqrtf((float)(e.n - 1));
         float* m0p = TCF(macc) + e.f;
-        float* m1p = m0p + (size_t)a.lay.mrows * TCU;
+        float* m1p = m0p + (size_t)(a.lay.mrows + 1) * TCU;
         float* dst = e.Mg() + (size_t)win * e.ND * TCU + e.f;
         for (int rr = hh; rr < rows; rr += 2) {
           dst[(size_t)rr * TCU] = (m0p[rr * TCU] + m1p[rr * TCU]) * inv_sqrt_nb;
@@ -830,34 +877,34 @@ struct EngineTC {
       e.epi_bar();
       const float bpv = bp.bp[0];
       float* cd = TCF(cdbuf) + s * 384;
-      for (int idx = e.tid; idx < 128 * dim; idx += TC_EPI) {
-        const int col = idx / dim, cc = idx - col * dim;
+      // stage 1: one (column, coordinate) contribution per thread
+      for (int cc = 0; cc < dim; ++cc) {
+        const int col = e.tid & 127;
+        if ((e.tid >> 7) != (cc & 1)) continue;     // halves of the CTA alternate over the coordinates
         const uint32_t cw = TCW(colw)[s * 128 + col];
         float val = 0.f;
         if ((cw & CW_VALID) && !(cw & CW_DUP)) {
           const int ed = cw_gid(cw), q = cw_q(cw);
-          const int i = ed / (n - 1), jj = ed - i * (n - 1);
-          int j = i + 1 + jj; if (j >= n) j -= n;
+          const int ijk = TCI(colijk)[s * 128 + col];
+          const int i = ijk & 31, j = (ijk >> 5) & 31, k = ijk >> 10;
           const float* p4 = pd + (4 * (col >> 6)) * 64;
           const int cl = col & 63, pc = cw_pc(cw);
           const float pg = (p4[pc] + p4[64 + pc]) + (p4[128 + pc] + p4[192 + pc]) + bpv;
           const float vc = TCF(egv)[ed * 3 + cc], inv = TCF(eginv)[ed];
           if (q == 0) {
             val = pg * vc * inv;
-          } else {
-            const int k = dirmap(ek, q - 1, i, j, dim);
-            if (ek != KIND_LAST || k == i * dim + cc) {
-              const float pdv = (p4[cl] + p4[64 + cl]) + (p4[128 + cl] + p4[192 + cl]);
-              const float vd = TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k];
-              const float ld = TCI(egiz)[ed] ? 0.f : TCF(colsd)[s * 128 + col] / (2.f * TCF(eglen)[ed]);
-              val = (pdv * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
-            }
+          } else if (ek != KIND_LAST || k == i * dim + cc) {
+            const float pdv = (p4[cl] + p4[64 + cl]) + (p4[128 + cl] + p4[192 + cl]);
+            const float vd = TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k];
+            const float ld = TCI(egiz)[ed] ? 0.f : TCF(colsd)[s * 128 + col] / (2.f * TCF(eglen)[ed]);
+            val = (pdv * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
           }
         }
         cd[col * 3 + cc] = val;
       }
       e.epi_bar();
       {
+        // stage 2: fixed-order sums over the edges of a receiver
         const int r = ek == KIND_MID ? e.ND : ek == KIND_LAST ? 1 + dim : 1 + 2 * dim;
         const int g0 = e.hdr(s, TH_G0), ng = e.hdr(s, TH_NG), i_first = e.hdr(s, TH_IFIRST), i_last = e.hdr(s, TH_ILAST);
         const int per = r * dim;
@@ -891,7 +938,7 @@ struct EngineTC {
 
   // ---- one evaluation of (f, div f) at time t for the positions in xin (shared memory, D floats) ----
   __device__ __forceinline__ void eval(float t, const float* xin, const int32_t* feat, float* fout) {
-    if (is_epi) {
+    {
       if (tid < dim) {
         float s = 0.f;
         for (int i = 0; i < n; ++i) s += xin[i * dim + tid];
@@ -924,6 +971,7 @@ struct EngineTC {
       }
       epi_bar();
     }
+#pragma unroll 1
     for (int b = 0; b < m.nblocks; ++b) {
       const bool last = (b == m.nblocks - 1);
       const bool htan = b > 0;
@@ -934,19 +982,19 @@ struct EngineTC {
         NodePre p{*this, b, a.tabs.cnt[kind], last ? 3 : 4, kind};
         run_phase(p);
       }
-      if (is_epi) epi_bar();     // P_s / P_r / P_h / h_in of every node are in global memory
+      epi_bar();     // P_s / P_r / P_h / h_in of every node are in global memory
       pend(P_NODE_PRE);
       {
         EdgePh p{*this, b, a.tabs.cnt[ekind], 2 * m.L - 1, ekind, htan, 0.f, 0.f, 0.f};
         run_phase(p);
       }
-      if (is_epi) epi_bar();     // coordinate accumulators and aggregated messages complete
+      epi_bar();     // coordinate accumulators and aggregated messages complete
       pend(P_EDGE);
       if (!last) {
         NodePost p{*this, b, a.tabs.cnt[TT_NODE], m.L + 1, TT_NODE, htan};
         run_phase(p);
       }
-      if (is_epi) {
+      {
         epi_bar();
         const float invnb = 1.f / (float)(n - 1);
         for (int i = tid; i < D; i += TC_EPI) TCF(xs)[i] += TCF(xacc)[i] * invnb;
@@ -956,7 +1004,7 @@ struct EngineTC {
       }
       pend(P_NODE_POST);
     }
-    if (is_epi) {
+    {
       const float fs = m.final_scaling[0];
       for (int i = tid; i < D; i += TC_EPI) fout[i] = (TCF(xs)[i] - TCF(xs0)[i] - TCF(mu)[i % dim]) * fs;
       if (tid == 0) {

@@ -9,7 +9,7 @@ from ecnf_b200.engine import PackedParams
 from ecnf_b200.nets.egnn import init_flat_params
 
 NAMES = ["node_pre", "edge", "node_post", "  wait_mma(epi)", "  build", "  epilogue", "  messages", "  coords", "  weight_load", "  tile_meta",
-         "  issue_warp_wait", "misc"]
+         "  issue_warp_wait", "misc", "  epi_ld", "  epi_act", "  epi_st", "  arrive", "  build_gather"]
 NTOP = 3
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 cnf = build_cnf(13, 3, 0.01, 1.0, 3, (128, 128, 128), 64, 8, 1)
