@@ -19,9 +19,9 @@
 //   * every Dense layer is 3 x (K/16) tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-17 relative per
 //     product, measured 4e-6 by tools/probe_tc2.cu) -- single-pass bf16/tf32 misses the 1e-4 tolerance on log q;
 //   * two tiles are in flight (two accumulators, two B buffers): while the epilogue threads work on one, the tensor
-//     core multiplies the other.  There is no CTA barrier in the layer chain: every thread counts itself in on a
-//     shared-memory arrival counter when its part of the next operand is written, the LAST one to arrive issues the
-//     MMAs, and tcgen05.commit -> mbarrier "done[s]" hands the accumulator back to the threads;
+//     core multiplies the other.  A dedicated warp issues the MMAs (the issuing thread blocks while the tensor-core
+//     queue is full, which must not hold up an epilogue warp); hand-over is by mbarriers only
+//     (epilogue threads -> "ready[s]" -> issue warp -> tcgen05.commit -> "done[s]" -> epilogue threads);
 //   * the only cross-lane work are the two Dense(1) heads (attention logit, coordinate head): a 62-shuffle transposing
 //     butterfly per warp + one 4-way sum through shared memory;
 //   * tile composition (which (group, slot) sits in which column) is precomputed per (n, dim, kind) into a table.
@@ -34,8 +34,11 @@ namespace ecnf_solve_detail {
 using namespace ecnf_tc;
 
 constexpr int TCU = 128, TCH = 64;
-constexpr int TC_NT = 256;          // 8 warps: thread (f, hh) owns feature / TMEM lane f and the column half hh
-constexpr int TC_EPI = TC_NT;
+constexpr int TC_NT = 288;          // 8 epilogue warps (thread (f, hh) owns feature / TMEM lane f and the column half hh) + 1 MMA-issue warp
+constexpr int TC_EPI = 256;
+#ifndef TC_WPREFETCH
+#define TC_WPREFETCH 0
+#endif
 constexpr int TC_BOP = 65536;       // one B-operand buffer: hi image [K = 128][N = 128] + lo image
 constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;
 constexpr int TC_WCOL = 256;        // first TMEM column of the weight buffers (accumulators: [0, 128) and [128, 256))
@@ -204,9 +207,10 @@ struct EngineTC {
   const TcImages& img;
   const int n, dim, D, ND, E;
   const int tid, f, hh, warp, lane;
+  const bool is_epi;
   uint32_t tmem;         // TMEM base address
   uint32_t lane_addr;    // (32 * (warp & 3)) << 16
-  uint32_t ph0, ph1;     // completed-phase counters of done[0], done[1]
+  uint32_t ph0, ph1;     // phase counters of the two slots (ready[] for the issue warp, done[] for the epilogue threads)
 
   enum { P_NODE_PRE, P_EDGE, P_NODE_POST, P_WAIT, P_BUILD, P_EPI, P_MSG, P_COORD, P_WLOAD, P_META, P_CTRL_WAIT, P_MISC,
          P_EPI_LD, P_EPI_ACT, P_EPI_ST, P_ARRIVE, P_GATHER, P_NCOUNT };
@@ -216,7 +220,7 @@ struct EngineTC {
   __device__ __forceinline__ void pbeg() { prof_t0 = clock64(); }
   __device__ __forceinline__ void pend(int k) { const long long t1 = clock64(); if (tid == 0) prof_s()[k] += t1 - prof_t0; prof_t0 = t1; }
   __device__ __forceinline__ void qbeg() { prof_t1 = clock64(); }
-  __device__ __forceinline__ void qend(int k) { const long long t1 = clock64(); if (tid == 0) prof_s()[k] += t1 - prof_t1; prof_t1 = t1; }
+  __device__ __forceinline__ void qend(int k) { const long long t1 = clock64(); if (tid == 0 || tid == TC_EPI) prof_s()[k] += t1 - prof_t1; prof_t1 = t1; }
 #else
   __device__ __forceinline__ void pbeg() {}
   __device__ __forceinline__ void pend(int) {}
@@ -226,7 +230,7 @@ struct EngineTC {
 
   __device__ __forceinline__ float* ode_ptr() const { return TCF(ode); }
   __device__ __forceinline__ float* red_ptr() const { return TCF(red); }
-  __device__ __forceinline__ uint32_t* arrivals(int s) const { return reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars) + s; }
+  __device__ __forceinline__ uint64_t* bar_ready(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + s; }
   __device__ __forceinline__ uint64_t* bar_done(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + 2 + s; }
   __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars + 32); }
   // per-CTA global scratch (L2 resident): h, h_in [n][ND][H]; P_s, P_r, aggregated messages, P_h [n][ND][U]
@@ -240,9 +244,9 @@ struct EngineTC {
   __device__ __forceinline__ EngineTC(const KernelArgs& a_)
       : a(a_), m(a_.m), img(a_.img), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim), ND(1 + a_.m.n * a_.m.dim),
         E(a_.m.n * (a_.m.n - 1)), tid(threadIdx.x), f(threadIdx.x & 127), hh((threadIdx.x >> 7) & 1), warp(threadIdx.x >> 5),
-        lane(threadIdx.x & 31) {
+        lane(threadIdx.x & 31), is_epi(threadIdx.x < TC_EPI) {
     if (tid == 0) {
-      *arrivals(0) = 0u; *arrivals(1) = 0u;
+      mbar_init(bar_ready(0), TC_EPI); mbar_init(bar_ready(1), TC_EPI);
       mbar_init(bar_done(0), 1); mbar_init(bar_done(1), 1);
 #ifdef ECNF_TC_PROFILE
       for (int k = 0; k < P_NCOUNT; ++k) prof_s()[k] = 0;
@@ -256,7 +260,7 @@ struct EngineTC {
     tmem = *tmem_slot();
     lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     ph0 = ph1 = 0;
-    {   // accumulators start finite (columns beyond a tile's N are read but never used)
+    if (is_epi) {   // accumulators start finite (columns beyond a tile's N are read but never used)
       uint32_t z[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) z[c] = 0u;
@@ -278,50 +282,47 @@ struct EngineTC {
     if (warp == 0) tmem_dealloc(tmem, 512);
   }
 
-  // ---- hand-over between the threads and the tensor core ------------------------------------------------------------
-  __device__ __forceinline__ void epi_bar() const { __syncthreads(); }
-  __device__ __forceinline__ void wait_done(int s) {
-    qbeg();
+  // ---- hand-over between the epilogue threads and the MMA-issue warp ----------------------------------------------
+  __device__ __forceinline__ void epi_bar() const { named_bar_sync(1, TC_EPI); }
+  __device__ __forceinline__ void wait_slot(uint64_t* bar, int s) {
     const uint32_t par = (s ? ph1 : ph0) & 1u;
-    mbar_wait(bar_done(s), par);
+    mbar_wait(bar, par);
     ph0 += (s == 0); ph1 += (s != 0);
     tc_fence_after();
-    qend(P_WAIT);
   }
-  // acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s] (K x N), 3-pass split; commit -> done[s].  One thread.
-  __device__ __forceinline__ void issue_mma(int s, uint32_t a_col, int K, int N) {
-    const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_B_MN;
-    const uint32_t bsm = smem_u32(smem_tc + a.lay.bop) + (uint32_t)s * TC_BOP;
-    uint64_t bh = make_sdesc(bsm, TC_LBO, TC_SBO);
-    uint64_t bl = make_sdesc(bsm + 32768u, TC_LBO, TC_SBO);
-    const uint32_t acc = tmem + 128u * s;
-    uint32_t a_hi = tmem + a_col, a_lo = tmem + a_col + (uint32_t)(K >> 1);
-    const int nk = K >> 4;
-    mma_ts(acc, a_hi, bh, idesc, 0u);
-    mma_ts(acc, a_lo, bh, idesc, 1u);
-    mma_ts(acc, a_hi, bl, idesc, 1u);
-    for (int ks = 1; ks < nk; ++ks) {
-      bh += (2u * TC_LBO) >> 4; bl += (2u * TC_LBO) >> 4; a_hi += 8; a_lo += 8;
-      mma_ts(acc, a_hi, bh, idesc, 1u);
-      mma_ts(acc, a_lo, bh, idesc, 1u);
-      mma_ts(acc, a_hi, bl, idesc, 1u);
-    }
-    mma_commit(bar_done(s));
-  }
-  // My part of slot s's next operands (B in shared memory, weights / drained accumulator in TMEM) is complete.  The
-  // arrival counter is an acq_rel read-modify-write chain: the thread that completes the count of TC_NT has every
-  // other thread's writes ordered before it and issues the layer.
-  __device__ __forceinline__ void hand_over(int s, uint32_t a_col, int K) {
+  __device__ __forceinline__ void wait_done(int s) { qbeg(); wait_slot(bar_done(s), s); qend(P_WAIT); }
+  // epilogue threads: my part of slot s's next operands (B in shared memory, weights / drained accumulator in TMEM) is complete
+  __device__ __forceinline__ void arrive_ready(int s) {
     qbeg();
     fence_proxy_async();
     tc_fence_before();
-    uint32_t old;
-    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(arrivals(s))) : "memory");
-    if ((old & (TC_NT - 1)) == TC_NT - 1) {
-      tc_fence_after();
-      issue_mma(s, a_col, K, hdr(s, TH_N));
-    }
+    mbar_arrive(bar_ready(s));
     qend(P_ARRIVE);
+  }
+  // issue warp: wait for all epilogue threads, then acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s]
+  // (K x N), 3-pass split; commit -> done[s]
+  __device__ __forceinline__ void issue_mma(int s, uint32_t a_col, int K) {
+    if (lane == 0) {
+      wait_slot(bar_ready(s), s);
+      const int N = hdr(s, TH_N);
+      const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_B_MN;
+      const uint32_t bsm = smem_u32(smem_tc + a.lay.bop) + (uint32_t)s * TC_BOP;
+      uint64_t bh = make_sdesc(bsm, TC_LBO, TC_SBO);
+      uint64_t bl = make_sdesc(bsm + 32768u, TC_LBO, TC_SBO);
+      const uint32_t acc = tmem + 128u * s;
+      uint32_t a_hi = tmem + a_col, a_lo = tmem + a_col + (uint32_t)(K >> 1);
+      const int nk = K >> 4;
+      mma_ts(acc, a_hi, bh, idesc, 0u);
+      mma_ts(acc, a_lo, bh, idesc, 1u);
+      mma_ts(acc, a_hi, bl, idesc, 1u);
+      for (int ks = 1; ks < nk; ++ks) {
+        bh += (2u * TC_LBO) >> 4; bl += (2u * TC_LBO) >> 4; a_hi += 8; a_lo += 8;
+        mma_ts(acc, a_hi, bh, idesc, 1u);
+        mma_ts(acc, a_lo, bh, idesc, 1u);
+        mma_ts(acc, a_hi, bl, idesc, 1u);
+      }
+      mma_commit(bar_done(s));
+    }
   }
 
   // ---- per-thread column helpers (thread (f, hh): feature f, columns [64 hh, +64) of slot s) -----------------------
@@ -454,16 +455,18 @@ struct EngineTC {
     const int ntiles = p.ntiles, NL = p.NL;
     const int npairs = (ntiles + 1) >> 1;
     const int total_q = npairs * NL;
-    p.prologue();
-    if (p.stream) {
-      load_w<TCU>(p.wimg(0), TC_WCOL);
-      if (total_q > 1) load_w<TCU>(p.wimg(1 % NL), TC_WCOL + 128);
+    if (is_epi) {
+      p.prologue();
+      if (p.stream) {
+        load_w<TCU>(p.wimg(0), TC_WCOL);
+        if (total_q > 1) load_w<TCU>(p.wimg(1 % NL), TC_WCOL + 128);
+      }
     }
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
       if (s >= ntiles) continue;
-      p.build(s, s);
-      hand_over(s, p.a_col(0, 0), p.K(0));
+      if (is_epi) { p.build(s, s); arrive_ready(s); }
+      else issue_mma(s, p.a_col(0, 0), p.K(0));
     }
     int q = 0;
 #pragma unroll 1
@@ -476,16 +479,26 @@ struct EngineTC {
           if (tile >= ntiles) continue;
           const bool last_slot = (s == 1) || (tile + 1 >= ntiles);
           const int ntile = tile + 2;
-          // the weights two layers ahead go into the buffer that layer q's MMAs (complete once done[last slot]
-          // fires) have been reading: fetch them into registers before the wait, store after it
-          const bool do_w = p.stream && last_slot && q + 2 < total_q;
-          uint32_t wv[2][TCU / 4];
-          if (do_w) fetch_w<TCU>(p.wimg((w + 2) % NL), wv);
-          wait_done(s);
-          if (do_w) { qbeg(); store_w<TCU>(wv, TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
-          p.epi(s, tile, w);
-          if (w < NL - 1) hand_over(s, p.a_col(q + 1, w + 1), p.K(w + 1));
-          else if (ntile < ntiles) { p.build(s, ntile); hand_over(s, p.a_col(q + 1, 0), p.K(0)); }
+          if (is_epi) {
+            // the weights two layers ahead go into the buffer that layer q's MMAs (complete once done[last slot]
+            // fires) have been reading: fetch them into registers before the wait, store after it
+            const bool do_w = p.stream && last_slot && q + 2 < total_q;
+#if TC_WPREFETCH
+            uint32_t wv[2][TCU / 4];
+            if (do_w) fetch_w<TCU>(p.wimg((w + 2) % NL), wv);
+            wait_done(s);
+            if (do_w) { qbeg(); store_w<TCU>(wv, TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
+#else
+            wait_done(s);
+            if (do_w) { qbeg(); load_w<TCU>(p.wimg((w + 2) % NL), TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
+#endif
+            p.epi(s, tile, w);
+            if (w < NL - 1) arrive_ready(s);
+            else if (ntile < ntiles) { p.build(s, ntile); arrive_ready(s); }
+          } else {
+            if (w < NL - 1) issue_mma(s, p.a_col(q + 1, w + 1), p.K(w + 1));
+            else if (ntile < ntiles) issue_mma(s, p.a_col(q + 1, 0), p.K(0));
+          }
         }
       }
     }
@@ -842,11 +855,17 @@ struct EngineTC {
           const bool st = ((segs >> ch) & 1u) != 0u;     // a new edge starts here: its primal message and gate
           curm = st ? v[8 * ch] : curm;
           eg = st ? wa_[8 * ch] : eg;
+          // the 8 columns of a chunk belong to one edge: distinct accumulator rows (padding shares the dump row), so
+          // the loads need not wait for the stores
+          float x[8], old[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int c = 8 * ch + u;
-            mac[mr_[c]] += fmaf(curm, wb_[c], v[c] * eg);
+            x[u] = fmaf(curm, wb_[c], v[c] * eg);
+            old[u] = mac[mr_[c]];
           }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) mac[mr_[8 * ch + u]] = old[u] + x[u];
         }
       }
       if (e.hdr(s, TH_FLUSH)) {
@@ -938,7 +957,7 @@ struct EngineTC {
 
   // ---- one evaluation of (f, div f) at time t for the positions in xin (shared memory, D floats) ----
   __device__ __forceinline__ void eval(float t, const float* xin, const int32_t* feat, float* fout) {
-    {
+    if (is_epi) {
       if (tid < dim) {
         float s = 0.f;
         for (int i = 0; i < n; ++i) s += xin[i * dim + tid];
@@ -982,19 +1001,19 @@ struct EngineTC {
         NodePre p{*this, b, a.tabs.cnt[kind], last ? 3 : 4, kind};
         run_phase(p);
       }
-      epi_bar();     // P_s / P_r / P_h / h_in of every node are in global memory
+      if (is_epi) epi_bar();     // P_s / P_r / P_h / h_in of every node are in global memory
       pend(P_NODE_PRE);
       {
         EdgePh p{*this, b, a.tabs.cnt[ekind], 2 * m.L - 1, ekind, htan, 0.f, 0.f, 0.f};
         run_phase(p);
       }
-      epi_bar();     // coordinate accumulators and aggregated messages complete
+      if (is_epi) epi_bar();     // coordinate accumulators and aggregated messages complete
       pend(P_EDGE);
       if (!last) {
         NodePost p{*this, b, a.tabs.cnt[TT_NODE], m.L + 1, TT_NODE, htan};
         run_phase(p);
       }
-      {
+      if (is_epi) {
         epi_bar();
         const float invnb = 1.f / (float)(n - 1);
         for (int i = tid; i < D; i += TC_EPI) TCF(xs)[i] += TCF(xacc)[i] * invnb;
@@ -1004,7 +1023,7 @@ struct EngineTC {
       }
       pend(P_NODE_POST);
     }
-    {
+    if (is_epi) {
       const float fs = m.final_scaling[0];
       for (int i = tid; i < D; i += TC_EPI) fout[i] = (TCF(xs)[i] - TCF(xs0)[i] - TCF(mu)[i % dim]) * fs;
       if (tid == 0) {
