@@ -37,6 +37,8 @@ LJ13 = dict(n_frames=13, dim=3, sigma_min=0.01, base_scale=1.0, n_blocks_egnn=3,
 QM9 = dict(n_frames=19, dim=3, sigma_min=1e-6, base_scale=2.0, n_blocks_egnn=5, mlp_units=(256, 256, 256, 256),
            n_invariant_feat_hidden=32, time_embedding_dim=8, n_features=1)
 N_EVALS_FIXED = 121          # 1 FSAL init + 6 stages x 20 steps (dt = 0.05)
+# one ncu --set full capture of ecnf_solve_tc_kernel (profiles/r1_solve_tc_full.txt): dram read + write bytes per trajectory
+NCU_DRAM_BYTES_PER_TRAJ = None
 METRIC = "LJ13 samples/s with exact log-q (Dopri5)"
 UNIT = "samples/s"
 
@@ -338,10 +340,14 @@ def main():
                        "n_evals_per_sample": evals_per_launch / B, "params": "synthetic stiffened init (seed 0)",
                        "l2": "256 MiB flush buffer written between timed steps", "parallelism": f"dp{world} (independent trajectories; ESS statistics all-gathered)"},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None, "kernel": "ecnf_solve_kernel<128,64,div>",
+                         "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_TRAJ * B if NCU_DRAM_BYTES_PER_TRAJ else None,
+                         "kernel": "ecnf_solve_tc_kernel (tcgen05 + TMEM, 3-pass bf16 split, fp32 accumulate)",
                          "kernel_ms": k_ms, "algorithmic_flops_per_launch": alg_flops,
-                         "peak_source": f"{pk_kind} bf16 dense sustained (MEASURED_PEAKS.json); the kernel itself is fp32 SIMT this round",
-                         "fp32_fma_frac_of_nominal": achieved_tf / 74.5},
+                         "executed_tensor_flops_per_launch": evals_per_launch * int(eng.lib.ecnf_solve_tensor_flops_per_eval(eng.handle)),
+                         "peak_source": f"{pk_kind} bf16 dense sustained (MEASURED_PEAKS.json); numerator = algorithmic "
+                                        "(1+D)*F_fwd per evaluation (SURVEY 8(d)); the kernel executes 3 bf16 passes over "
+                                        "a structurally reduced tangent set, see executed_tensor_flops_per_launch",
+                         "traffic_source": "profiles/r1_solve_tc_full.txt: dram bytes of one ncu --set full capture, per trajectory x batch"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 39 * 4 + B * 13 * 4,
                     "d2h_bytes_per_step": B * 39 * 4 + B * 4 + 20},

@@ -86,6 +86,11 @@ int64_t ecnf_solve_workspace_bytes(const ecnf_model* m, int mode, int64_t B) {
   return 256 + (int64_t)grid_for(m, B < 1 ? 1 : B) * stride * (int64_t)sizeof(float) + (tc_eligible(m, div) ? tc_image_bytes(m) : 0);
 }
 
+int64_t ecnf_solve_tensor_flops_per_eval(const ecnf_model* m) {
+  if (!m || !use_tc(m, true)) return 0;
+  return tc_flops_per_eval(m);
+}
+
 int ecnf_set_engine(int engine) {
   if (engine != 0 && engine != 1) { ecnf_set_error("ecnf_set_engine: 0 = auto, 1 = fp32 SIMT"); return ECNF_ERR_INVALID; }
   g_engine = engine;

@@ -1,4 +1,6 @@
 // Tensor-core (tcgen05 / TMEM) instantiation of engine A + its weight-image preparation.
+#include <vector>
+
 #include "ecnf_solve_tc.cuh"
 
 namespace ecnf_solve_detail {
@@ -59,6 +61,27 @@ int64_t tables_bytes(const TcTabs& t) { return (int64_t)(t.off[TT_COUNT - 1] + t
 int64_t images_bytes(const ecnf_model* mdl) { return (walk_images(mdl, nullptr, nullptr) + 255) & ~255LL; }
 
 int64_t tc_image_bytes(const ecnf_model* mdl) { return images_bytes(mdl) + ((tables_bytes(make_tabs(mdl)) + 255) & ~255LL); }
+
+int64_t tc_flops_per_eval(const ecnf_model* mdl) {
+  const ecnf_config& c = mdl->cfg;
+  int64_t sumN[TT_COUNT];
+  for (int k = 0; k < TT_COUNT; ++k) {
+    const int cnt = tc_pack(k, c.n_frames, c.dim, nullptr);
+    std::vector<uint32_t> buf((size_t)cnt * TC_TILE_WORDS);
+    tc_pack(k, c.n_frames, c.dim, buf.data());
+    sumN[k] = 0;
+    for (int t = 0; t < cnt; ++t) sumN[k] += buf[(size_t)t * TC_TILE_WORDS + 192 + TH_N];
+  }
+  auto layer = [](int64_t n_cols, int K) { return 3 * 2 * (int64_t)128 * n_cols * K; };   // hi*hi + lo*hi + hi*lo
+  int64_t fl = 0;
+  for (int b = 0; b < c.n_blocks; ++b) {
+    const bool last = b == c.n_blocks - 1;
+    fl += (last ? 3 : 4) * layer(sumN[b > 0 ? TT_NODE : TT_NODE1], TCH);
+    fl += (2 * c.n_layers - 1) * layer(sumN[last ? TT_LAST : (b == 0 ? TT_FIRST : TT_MID)], TCU);
+    if (!last) fl += (c.n_layers + 1) * layer(sumN[TT_NODE], TCU);
+  }
+  return fl;
+}
 
 int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cudaStream_t st) {
   static TcPrepList list;   // filled per call below (host-side scratch; the call is not re-entrant across threads)

@@ -74,6 +74,9 @@ int64_t ecnf_solve_workspace_bytes(const ecnf_model* m, int mode, int64_t B);
  * shape is eligible: mlp_units 128, n_hidden 64, exact divergence; fp32 SIMT otherwise), 1 = always fp32 SIMT
  * (the accuracy reference).  Process-wide.                                                                  */
 int ecnf_set_engine(int engine);
+/* tcgen05 flops the tensor-core engine issues per vector-field evaluation with exact divergence (3 bf16 passes over
+ * every 128-lane x N-column tile-layer), 0 when the shape runs on the fp32 SIMT engine.  For roofline reports.   */
+int64_t ecnf_solve_tensor_flops_per_eval(const ecnf_model* m);
 
 int ecnf_vf_forward(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, int64_t B,
                     float* out_f, void* ws, int64_t ws_bytes, void* stream);
