@@ -286,7 +286,7 @@ struct EngineTC {
   __device__ __forceinline__ void epi_bar() const { named_bar_sync(1, TC_EPI); }
   __device__ __forceinline__ void wait_slot(uint64_t* bar, int s) {
     const uint32_t par = (s ? ph1 : ph0) & 1u;
-    mbar_wait(bar, par);
+    mbar_wait_parked(bar, par, 20000u);
     ph0 += (s == 0); ph1 += (s != 0);
     tc_fence_after();
   }
