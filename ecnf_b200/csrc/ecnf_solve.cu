@@ -91,6 +91,11 @@ int64_t ecnf_solve_tensor_flops_per_eval(const ecnf_model* m) {
   return tc_flops_per_eval(m);
 }
 
+int ecnf_solve_tc_tile_table(const ecnf_model* m, int kind, uint32_t* out_host, int64_t cap_words) {
+  if (!m || !tc_eligible(m, true)) return 0;
+  return tc_tile_table(m, kind, out_host, cap_words);
+}
+
 int ecnf_set_engine(int engine) {
   if (engine != 0 && engine != 1) { ecnf_set_error("ecnf_set_engine: 0 = auto, 1 = fp32 SIMT"); return ECNF_ERR_INVALID; }
   g_engine = engine;

@@ -61,6 +61,7 @@ int launch_t(const ecnf_model* mdl, KernelArgs& a, int grid, cudaStream_t st);
 bool tc_eligible(const ecnf_model* mdl, bool div);
 int64_t tc_image_bytes(const ecnf_model* mdl);
 int64_t tc_flops_per_eval(const ecnf_model* mdl);
+int tc_tile_table(const ecnf_model* mdl, int kind, uint32_t* out, int64_t cap_words);
 int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cudaStream_t st);
 
 }  // namespace ecnf_solve_detail

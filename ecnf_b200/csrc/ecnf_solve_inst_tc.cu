@@ -83,6 +83,13 @@ int64_t tc_flops_per_eval(const ecnf_model* mdl) {
   return fl;
 }
 
+int tc_tile_table(const ecnf_model* mdl, int kind, uint32_t* out, int64_t cap_words) {
+  if (kind < 0 || kind >= TT_COUNT) return 0;
+  const int cnt = tc_pack(kind, mdl->cfg.n_frames, mdl->cfg.dim, nullptr);
+  if (out && (int64_t)cnt * TC_TILE_WORDS <= cap_words) tc_pack(kind, mdl->cfg.n_frames, mdl->cfg.dim, out);
+  return cnt;
+}
+
 int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cudaStream_t st) {
   static TcPrepList list;   // filled per call below (host-side scratch; the call is not re-entrant across threads)
   TcPrepList local{};

@@ -77,6 +77,12 @@ int ecnf_set_engine(int engine);
 /* tcgen05 flops the tensor-core engine issues per vector-field evaluation with exact divergence (3 bf16 passes over
  * every 128-lane x N-column tile-layer), 0 when the shape runs on the fp32 SIMT engine.  For roofline reports.   */
 int64_t ecnf_solve_tensor_flops_per_eval(const ecnf_model* m);
+/* Host copy of the tensor-core engine's tile table of one kind (0 node/primal-only, 1 node, 2 first-block edges,
+ * 3 middle-block edges, 4 last-block edges): 240 uint32 per tile (128 column words: bit31 valid, bit30 primal, bit29
+ * repeated primal, [0,10) group, [10,18) slot, [18,24) primal column of the segment; 64 group words; 16 header words
+ * from word 192: columns per half, MMA N, first group, groups, window, flush, receivers, segment-start mask; 4 primal masks from word 224).
+ * Returns the number of tiles (writes at most cap_words), 0 when the shape is not eligible.  Test / debug aid.      */
+int ecnf_solve_tc_tile_table(const ecnf_model* m, int kind, uint32_t* out_host, int64_t cap_words);
 
 int ecnf_vf_forward(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, int64_t B,
                     float* out_f, void* ws, int64_t ws_bytes, void* stream);
