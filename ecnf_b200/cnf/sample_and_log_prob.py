@@ -3,7 +3,7 @@ jax.vmap-ed (setup_training.py:47,197) or lax.scan-ned (setup_training.py:180); 
 accepted directly and every trajectory runs its own adaptive Dopri5 loop on the GPU.
 
 Differences, all documented in DESIGN.md:
-  * `approx=True` (Hutchinson) is not built yet -> EcnfError;
+  * `approx=True` runs the Hutchinson estimator with one fixed probe per trajectory (`eps=` injects it);
   * noise can be injected (`x0=`) so parity tests bypass the RNG; without it the base draw comes from the
     library's Philox stream keyed by (key, global sample index), not from jax threefry;
   * the fixed-step branch of sample_and_log_prob_cnf integrates (x0, 0) -- the reference passes y0=x0 there and
@@ -47,27 +47,28 @@ def sample_cnf(cnf: FlowMatchingCNF, params, key, features=None, use_fixed_step_
 
 def get_log_prob(cnf: FlowMatchingCNF, params, x, key=None, features=None, approx: bool = False,
                  use_fixed_step_size: bool = False, rtol: float = 1e-5, atol: float = 1e-5, step_size: float = 0.05,
-                 *, return_stats: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """ecnf/cnf/sample_and_log_prob.py:41-94 (exact branch): returns (log_p, log_prob_base, delta)."""
-    if approx:
-        raise L.EcnfError("approx=True (Hutchinson estimator) is not implemented in ecnf_b200 yet")
+                 *, eps=None, global_offset: int = 0, return_stats: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """ecnf/cnf/sample_and_log_prob.py:41-94: returns (log_p, log_prob_base, delta).  approx=True = the Hutchinson
+    branch (:69-78): one probe eps ~ N(0, I) per trajectory, drawn once from `key` (:55) -- or injected with `eps=`."""
     eng = cnf.engine
     x = torch.as_tensor(x, dtype=torch.float32, device=eng.device)
     single = x.dim() == 1
     x = x.reshape(-1, eng.cfg.D)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
-    _, logs, stats = eng.solve(params, L.MODE_LOGPROB, x, features, ctrl)
+    if approx and eps is None:
+        eps = eng.normal_noise(key, x.shape[0], global_offset, substream=1)
+    _, logs, stats = eng.solve(params, L.MODE_LOGPROB, x, features, ctrl, eps=eps if approx else None)
     out = (logs[0, 0], logs[0, 1], logs[0, 2]) if single else (logs[:, 0], logs[:, 1], logs[:, 2])
     return (*out, stats) if return_stats else out
 
 
 def sample_and_log_prob_cnf(cnf: FlowMatchingCNF, params, key, features=None, approx: bool = False,
                             use_fixed_step_size: bool = False, rtol: float = 1e-5, atol: float = 1e-5,
-                            step_size: float = 0.05, *, n_samples: Optional[int] = None, x0=None,
+                            step_size: float = 0.05, *, n_samples: Optional[int] = None, x0=None, eps=None,
                             global_offset: int = 0, return_stats: bool = False):
-    """ecnf/cnf/sample_and_log_prob.py:97-149 (exact branch): returns (x1, log_q)."""
-    if approx:
-        raise L.EcnfError("approx=True (Hutchinson estimator) is not implemented in ecnf_b200 yet")
+    """ecnf/cnf/sample_and_log_prob.py:97-149: returns (x1, log_q).  approx=True = the Hutchinson branch (:123-133); the
+    reference draws its probe from the SAME key as the base sample (:130,137; SURVEY C#6), which here means the raw noise
+    underneath `sample_base(key)` (substream 0) -- or inject it with `eps=`."""
     eng = cnf.engine
     if x0 is not None:
         x0 = torch.as_tensor(x0, dtype=torch.float32, device=eng.device)
@@ -77,6 +78,8 @@ def sample_and_log_prob_cnf(cnf: FlowMatchingCNF, params, key, features=None, ap
         B, single = _batch(features, eng.cfg.n_frames, n_samples)
         x0 = eng.base_sample(key, B, global_offset)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
-    x1, logs, stats = eng.solve(params, L.MODE_SAMPLE_LOGQ, x0, features, ctrl)
+    if approx and eps is None:
+        eps = eng.normal_noise(key, x0.shape[0], global_offset, substream=0)
+    x1, logs, stats = eng.solve(params, L.MODE_SAMPLE_LOGQ, x0, features, ctrl, eps=eps if approx else None)
     out = (x1[0], logs[0, 0]) if single else (x1, logs[:, 0])
     return (*out, stats) if return_stats else out

@@ -69,6 +69,14 @@ __global__ void base_sample_kernel(uint64_t seed, int64_t goff, int64_t B, int n
   }
 }
 
+// plain N(0, 1) draws keyed by the global sample index (Hutchinson probes)
+__global__ void normal_kernel(uint64_t seed, int64_t goff, int64_t B, int D, float* __restrict__ out, uint32_t sub) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int64_t b = idx / D;
+  out[idx] = philox_normal(seed, (uint64_t)(goff + b), (int)(idx - b * D), sub);
+}
+
 __global__ void uniform_kernel(uint64_t seed, int64_t goff, int64_t B, float* __restrict__ out, uint32_t sub) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -239,6 +247,16 @@ int ecnf_base_sample(const ecnf_model* m, uint64_t seed, int64_t goff, int64_t B
   dim3 blk(32, 8);
   base_sample_kernel<<<(unsigned)((B + 7) / 8), blk, 0, (cudaStream_t)stream>>>(seed, goff, B, m->cfg.n_frames, m->cfg.dim,
                                                                               m->cfg.base_scale, nullptr, out, 0u);
+  ECNF_CHECK_CUDA(cudaGetLastError());
+  return ECNF_OK;
+}
+
+int ecnf_normal_noise(const ecnf_model* m, uint64_t seed, int64_t goff, int64_t B, uint32_t substream, float* out, void* stream) {
+  if (!m || !out || B < 0) { ecnf_set_error("ecnf_normal_noise: bad argument"); return ECNF_ERR_INVALID; }
+  if (B == 0) return ECNF_OK;
+  const int D = m->cfg.n_frames * m->cfg.dim;
+  const int64_t tot = B * D;
+  normal_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, goff, B, D, out, substream);
   ECNF_CHECK_CUDA(cudaGetLastError());
   return ECNF_OK;
 }

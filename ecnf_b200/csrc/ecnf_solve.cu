@@ -35,7 +35,7 @@ int64_t scratch_stride_of(const ecnf_model* m, bool div) {
 
 bool mode_div(int mode) { return mode == ECNF_MODE_VF_DIV || mode == ECNF_MODE_SAMPLE_LOGQ || mode == ECNF_MODE_LOGPROB; }
 
-int run(const ecnf_model* m, int mode, const float* x, const float* t, const int32_t* feat, int64_t B,
+int run(const ecnf_model* m, int mode, const float* x, const float* t, const int32_t* feat, const float* eps, int64_t B,
         const ecnf_solve_ctrl* ctrl, float* out_x, float* out_logs, int32_t* out_stats, void* ws, int64_t ws_bytes,
         void* stream) {
   if (!m || !x || !feat || !out_x || B < 0) {
@@ -50,6 +50,7 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool div = mode_div(mode);
+  const bool tc = use_tc(m, div) && !eps;   // Hutchinson probes run on the SIMT engine
   const int grid = grid_for(m, B);
   KernelArgs a;
   a.m = ecnf_make_dev(m, m->d_params);
@@ -58,6 +59,7 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
   a.x_init = x;
   a.t_in = t;
   a.feat = feat;
+  a.eps = div ? eps : nullptr;
   if (ctrl) a.ctrl = *ctrl;
   else a.ctrl = ecnf_solve_ctrl{0, 0.05f, 1e-5f, 1e-5f, 1e-5f, 4096, 0.9f, 0.2f, 10.f, 5.f};
   a.out_x = out_x;
@@ -68,7 +70,7 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
   a.scratch_stride = scratch_stride_of(m, div);
   a.img.base = nullptr;
   ECNF_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));
-  if (use_tc(m, div)) {
+  if (tc) {
     void* image_ws = reinterpret_cast<char*>(ws) + 256 + (int64_t)grid * a.scratch_stride * (int64_t)sizeof(float);
     return launch_tc(m, a, grid, image_ws, st);
   }
@@ -106,19 +108,32 @@ int ecnf_vf_forward(const ecnf_model* m, const float* x, const float* t, const i
                     void* ws, int64_t ws_bytes, void* stream) {
   if (B == 0) return ECNF_OK;
   if (!t) { ecnf_set_error("ecnf_vf_forward: t is null"); return ECNF_ERR_INVALID; }
-  return run(m, ECNF_MODE_VF, x, t, feat, B, nullptr, out_f, nullptr, nullptr, ws, ws_bytes, stream);
+  return run(m, ECNF_MODE_VF, x, t, feat, nullptr, B, nullptr, out_f, nullptr, nullptr, ws, ws_bytes, stream);
 }
 
 int ecnf_vf_forward_div(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, int64_t B,
                         float* out_f, float* out_div, void* ws, int64_t ws_bytes, void* stream) {
   if (B == 0) return ECNF_OK;
   if (!t || !out_div) { ecnf_set_error("ecnf_vf_forward_div: null argument"); return ECNF_ERR_INVALID; }
-  return run(m, ECNF_MODE_VF_DIV, x, t, feat, B, nullptr, out_f, out_div, nullptr, ws, ws_bytes, stream);
+  return run(m, ECNF_MODE_VF_DIV, x, t, feat, nullptr, B, nullptr, out_f, out_div, nullptr, ws, ws_bytes, stream);
+}
+
+int ecnf_vf_forward_hutchinson(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, const float* eps,
+                               int64_t B, float* out_f, float* out_div, void* ws, int64_t ws_bytes, void* stream) {
+  if (B == 0) return ECNF_OK;
+  if (!t || !out_div || !eps) { ecnf_set_error("ecnf_vf_forward_hutchinson: null argument"); return ECNF_ERR_INVALID; }
+  return run(m, ECNF_MODE_VF_DIV, x, t, feat, eps, B, nullptr, out_f, out_div, nullptr, ws, ws_bytes, stream);
 }
 
 int ecnf_solve(const ecnf_model* m, int mode, const float* x_init, const int32_t* feat, int64_t B,
                const ecnf_solve_ctrl* ctrl, float* out_x, float* out_logs, int32_t* out_stats, void* ws,
                int64_t ws_bytes, void* stream) {
+  return ecnf_solve_hutchinson(m, mode, x_init, feat, nullptr, B, ctrl, out_x, out_logs, out_stats, ws, ws_bytes, stream);
+}
+
+int ecnf_solve_hutchinson(const ecnf_model* m, int mode, const float* x_init, const int32_t* feat, const float* eps,
+                          int64_t B, const ecnf_solve_ctrl* ctrl, float* out_x, float* out_logs, int32_t* out_stats,
+                          void* ws, int64_t ws_bytes, void* stream) {
   if (mode != ECNF_MODE_SAMPLE && mode != ECNF_MODE_SAMPLE_LOGQ && mode != ECNF_MODE_LOGPROB) {
     ecnf_set_error("ecnf_solve: bad mode %d", mode);
     return ECNF_ERR_INVALID;
@@ -132,7 +147,7 @@ int ecnf_solve(const ecnf_model* m, int mode, const float* x_init, const int32_t
     ecnf_set_error("ecnf_solve: adaptive stepping needs rtol or atol > 0");
     return ECNF_ERR_INVALID;
   }
-  return run(m, mode, x_init, nullptr, feat, B, ctrl, out_x, out_logs, out_stats, ws, ws_bytes, stream);
+  return run(m, mode, x_init, nullptr, feat, eps, B, ctrl, out_x, out_logs, out_stats, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -42,6 +42,7 @@ struct KernelArgs {
   const float* x_init;   // [B, D]
   const float* t_in;     // [B] (VF modes)
   const int32_t* feat;   // [B, n]
+  const float* eps;      // [B, D] Hutchinson probes, or null for the exact trace
   ecnf_solve_ctrl ctrl;
   float* out_x;          // [B, D]   (VF modes: f)
   float* out_logs;       // [B, 3]   (VF_DIV: out_div [B])

@@ -64,7 +64,7 @@ struct Geo {
 // ------------------------------------------------------------------------------------------------
 struct SmemLayout {
   int X1, X2, Wb, G, xt, xtacc, dacc, xs, xs0, xacc, mu, rowdot, rowsd, gv, gs1, glen, ginv, ge, tau, cvec,
-      ode, red, rowslot, rowgrp, gi, gj, giz, total_floats;
+      ode, red, rowslot, rowgrp, gi, gj, giz, epsv, total_floats;
 };
 
 template <int U, int H>
@@ -101,6 +101,7 @@ __host__ __device__ inline SmemLayout make_layout(int n, int dim, bool div) {
   L.gi = take(G_::TR);
   L.gj = take(G_::TR);
   L.giz = take(G_::TR);
+  L.epsv = take(D);
   L.total_floats = o;
   return L;
 }
@@ -208,22 +209,25 @@ struct Engine {
   static constexpr int TR = G_::TR, LD = G_::LD, RT = G_::RT;
   static constexpr int NT = NTHREADS;
   const EcnfModelDev& m;
-  const int n, dim, D, ND, E;
+  // ntan = tangent directions carried: D (exact trace: the basis), 1 (Hutchinson: the probe eps), 0 (no divergence)
+  const bool hutch;
+  const int n, dim, D, ntan, ND, E;
   const int tid;
+  const float* eps_g;   // Hutchinson probe of the current trajectory (global, D floats)
   float *X1, *X2, *Wb, *G, *xt, *xtacc, *dacc, *xs, *xs0, *xacc, *mu, *rowdot, *rowsd, *gv, *gs1, *glen, *ginv,
-      *ge, *tau, *cvec, *ode, *red;
+      *ge, *tau, *cvec, *ode, *red, *epsv;
   int *rowslot, *rowgrp, *gi, *gj, *giz;
   float *hA, *hB, *Ps, *Pr, *Mg;  // global scratch (this CTA's), NOT read through the non-coherent path
 
-  __device__ Engine(const EcnfModelDev& m_, float* smem, float* scratch)
-      : m(m_), n(m_.n), dim(m_.dim), D(m_.n * m_.dim), ND(DIV ? 1 + m_.n * m_.dim : 1), E(m_.n * (m_.n - 1)),
-        tid(threadIdx.x) {
+  __device__ Engine(const EcnfModelDev& m_, float* smem, float* scratch, bool hutch_)
+      : m(m_), hutch(DIV && hutch_), n(m_.n), dim(m_.dim), D(m_.n * m_.dim),
+        ntan(DIV ? (hutch_ ? 1 : m_.n * m_.dim) : 0), ND(1 + ntan), E(m_.n * (m_.n - 1)), tid(threadIdx.x), eps_g(nullptr) {
     const SmemLayout L = make_layout<U, H>(n, dim, DIV);
     X1 = smem + L.X1; X2 = smem + L.X2; Wb = smem + L.Wb; G = smem + L.G; xt = smem + L.xt;
     xtacc = smem + L.xtacc; dacc = smem + L.dacc; xs = smem + L.xs; xs0 = smem + L.xs0; xacc = smem + L.xacc;
     mu = smem + L.mu; rowdot = smem + L.rowdot; rowsd = smem + L.rowsd; gv = smem + L.gv; gs1 = smem + L.gs1;
     glen = smem + L.glen; ginv = smem + L.ginv; ge = smem + L.ge; tau = smem + L.tau; cvec = smem + L.cvec;
-    ode = smem + L.ode; red = smem + L.red;
+    ode = smem + L.ode; red = smem + L.red; epsv = smem + L.epsv;
     rowslot = reinterpret_cast<int*>(smem + L.rowslot); rowgrp = reinterpret_cast<int*>(smem + L.rowgrp);
     gi = reinterpret_cast<int*>(smem + L.gi); gj = reinterpret_cast<int*>(smem + L.gj);
     giz = reinterpret_cast<int*>(smem + L.giz);
@@ -231,6 +235,7 @@ struct Engine {
     Mg = Pr + (size_t)n * ND * U;
   }
 
+  __device__ __forceinline__ void set_eps(const float* e) { eps_g = e; }
   __device__ __forceinline__ float* ode_ptr() const { return ode; }
   __device__ __forceinline__ float* red_ptr() const { return red; }
 
@@ -343,9 +348,11 @@ struct Engine {
   }
 
   // ---- edge phase of block b ----
-  __device__ void edge_phase(int b, int kind, bool htan) {
+  // lastb: last block (no messages / phi_h).  kind: tangent-row structure; with a Hutchinson probe every block is "MID"
+  // (one dense direction), also the last one, whose full coordinate tangent is then needed.
+  __device__ void edge_phase(int b, int kind, bool htan, bool lastb) {
     const EcnfBlockParams& bp = m.blk[b];
-    const int nact = !DIV ? 0 : (kind == KIND_MID ? D : kind == KIND_LAST ? dim : 2 * dim);
+    const int nact = !DIV ? 0 : (kind == KIND_MID ? ntan : kind == KIND_LAST ? dim : 2 * dim);
     const int r = 1 + nact;
     const int gpt = DIV ? min(TR / r, n - 1) : TR;
     const float inv_sqrt_nb = rsqrtf((float)(n - 1));
@@ -355,8 +362,8 @@ struct Engine {
     // zero the accumulators of this block
     for (int i = tid; i < D; i += NTHREADS) { xacc[i] = 0.f; dacc[i] = 0.f; }
     if (DIV && kind != KIND_LAST)
-      for (int i = tid; i < D * D; i += NTHREADS) xtacc[i] = 0.f;
-    if (kind != KIND_LAST)
+      for (int i = tid; i < D * ntan; i += NTHREADS) xtacc[i] = 0.f;
+    if (!lastb)
       for (int i = tid; i < n * ND * U; i += NTHREADS) Mg[i] = 0.f;
     __syncthreads();
 
@@ -398,7 +405,7 @@ struct Engine {
           const int k = dirmap(kind, q - 1, i, j, dim);
           float sd = 0.f;
           for (int c = 0; c < dim; ++c)
-            sd = fmaf(gv[g * 3 + c], xt[(i * dim + c) * D + k] - xt[(j * dim + c) * D + k], sd);
+            sd = fmaf(gv[g * 3 + c], xt[(i * dim + c) * ntan + k] - xt[(j * dim + c) * ntan + k], sd);
           rowslot[row] = 1 + k;
           rowsd[row] = giz[g] ? 0.f : 2.f * sd;
         }
@@ -436,7 +443,7 @@ struct Engine {
           tile_gemm<U, U, TR, LD, true>(X1, bp.We[l], Wb, acc, nrows);
           epi_act<U, TR, LD>(acc, bp.be[l], X1, nrows, r, rowgrp, G, DIV);
         }
-        if (kind != KIND_LAST) {
+        if (!lastb) {
           // attention gate + message aggregation (egnn.py:99-104)
           rowdot_tile(X1, bp.wa, nrows);
           if (tid < ng) ge[tid] = ecnf_sigmoid(rowdot[tid * r] + bav);
@@ -491,8 +498,8 @@ struct Engine {
       {
         const int i_first = e0 / (n - 1), i_last = (e0 + ng - 1) / (n - 1);
         const int nprim = (i_last - i_first + 1) * dim;
-        const int ntan = DIV ? (r - 1) * dim : 0;
-        for (int idx = tid; idx < nprim + ntan; idx += NTHREADS) {
+        const int nwork_tan = DIV ? (r - 1) * dim : 0;
+        for (int idx = tid; idx < nprim + nwork_tan; idx += NTHREADS) {
           if (idx < nprim) {
             const int ri = idx / dim, c = idx - ri * dim, i = i_first + ri;
             const int ga = max(e0, i * (n - 1)) - e0, gb = min(e0 + ng, (i + 1) * (n - 1)) - e0;
@@ -509,11 +516,11 @@ struct Engine {
               if (kind == KIND_LAST && k != i * dim + c) continue;
               const float pg = rowdot[g * r] + bpv, pd = rowdot[g * r + q];
               const float vc = gv[g * 3 + c], inv = ginv[g];
-              const float vd = xt[(i * dim + c) * D + k] - xt[(j * dim + c) * D + k];
+              const float vd = xt[(i * dim + c) * ntan + k] - xt[(j * dim + c) * ntan + k];
               const float ld = giz[g] ? 0.f : rowsd[g * r + q] / (2.f * glen[g]);
               const float cd = (pd * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
               if (kind == KIND_LAST) dacc[i * dim + c] += cd;
-              else xtacc[(i * dim + c) * D + k] += cd;
+              else xtacc[(i * dim + c) * ntan + k] += cd;
             }
           }
         }
@@ -544,12 +551,22 @@ struct Engine {
       xs[i] = v;
       xs0[i] = v;
     }
-    if (DIV) {
+    if (DIV && !hutch) {
       const float invn = 1.f / (float)n;
       for (int idx = tid; idx < D * D; idx += NTHREADS) {
         const int a = idx / D, k = idx - a * D;
         const int ia = a / dim, ca = a - ia * dim, ik = k / dim, ck = k - ik * dim;
         xt[idx] = (ca == ck) ? ((ia == ik ? 1.f : 0.f) - invn) : 0.f;
+      }
+    }
+    if (hutch) {
+      // tangent of the centred positions in the probe direction: eps - mean_nodes(eps)
+      for (int i = tid; i < D; i += NTHREADS) epsv[i] = eps_g[i];
+      __syncthreads();
+      for (int i = tid; i < D; i += NTHREADS) {
+        float mean = 0.f;
+        for (int node = 0; node < n; ++node) mean += epsv[node * dim + i % dim];
+        xt[i] = epsv[i] - mean / (float)n;
       }
     }
     for (int idx = tid; idx < n * H; idx += NTHREADS) {
@@ -561,24 +578,30 @@ struct Engine {
     __syncthreads();
     for (int b = 0; b < m.nblocks; ++b) {
       const bool last = (b == m.nblocks - 1);
-      const int kind = last ? KIND_LAST : (b == 0 ? KIND_FIRST : KIND_MID);
+      const int kind = hutch ? KIND_MID : (last ? KIND_LAST : (b == 0 ? KIND_FIRST : KIND_MID));
       const bool htan = DIV && b > 0;
       node_pre(b, htan);
-      edge_phase(b, kind, htan);
+      edge_phase(b, kind, htan, last);
       if (!last) node_post(b, htan);
       const float invnb = 1.f / (float)(n - 1);
       for (int i = tid; i < D; i += NTHREADS) xs[i] += xacc[i] * invnb;
-      if (DIV && !last)
-        for (int i = tid; i < D * D; i += NTHREADS) xt[i] += xtacc[i] * invnb;
+      if (DIV && (!last || hutch))
+        for (int i = tid; i < D * ntan; i += NTHREADS) xt[i] += xtacc[i] * invnb;
       __syncthreads();
     }
     const float fs = m.final_scaling[0];
     for (int i = tid; i < D; i += NTHREADS) fout[i] = (xs[i] - xs0[i] - mu[i % dim]) * fs;
     if (DIV && tid == 0) {
-      const float invnb = 1.f / (float)(n - 1);
       float s = 0.f;
-      for (int d = 0; d < D; ++d) s += xt[d * D + d] + dacc[d] * invnb;
-      fout[D] = fs * (s - (float)D);
+      if (hutch) {
+        // eps . (J eps): the output tangent is fs (x_L-dot - x0-dot - mean(eps)) = fs (xt - eps)   (egnn.py:183-188)
+        for (int d = 0; d < D; ++d) s = fmaf(epsv[d], xt[d] - epsv[d], s);
+        fout[D] = fs * s;
+      } else {
+        const float invnb = 1.f / (float)(n - 1);
+        for (int d = 0; d < D; ++d) s += xt[d * D + d] + dacc[d] * invnb;
+        fout[D] = fs * (s - (float)D);
+      }
     }
     __syncthreads();
   }
@@ -652,6 +675,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
     if (b >= a.B) break;
     const int32_t* feat = a.feat + b * eng.n;
     const float* xin = a.x_init + b * D;
+    eng.set_eps(a.eps ? a.eps + b * D : nullptr);
 
     int phase, stage = 0, n_steps = 0, n_acc = 0, n_evals = 0, status = 0;
     float tprev = T0, tnext = T0, dt = 0.f, h0 = 0.f, d1 = 0.f, t_eval, lp0_start = 0.f;
@@ -812,7 +836,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ecnf_solve_kernel(const __grid_co
   extern __shared__ __align__(16) float smem[];
   __shared__ long long s_traj;
   __shared__ float s_ctl[8];
-  Engine<U, H, DIV> eng(a.m, smem, a.scratch + (size_t)blockIdx.x * a.scratch_stride);
+  Engine<U, H, DIV> eng(a.m, smem, a.scratch + (size_t)blockIdx.x * a.scratch_stride, a.eps != nullptr);
   solve_body<Engine<U, H, DIV>, DIV>(a, eng, s_traj, s_ctl);
 }
 

@@ -228,6 +228,7 @@ struct EngineTC {
   __device__ __forceinline__ void qend(int) {}
 #endif
 
+  __device__ __forceinline__ void set_eps(const float*) {}   // Hutchinson probes run on the SIMT engine
   __device__ __forceinline__ float* ode_ptr() const { return TCF(ode); }
   __device__ __forceinline__ float* red_ptr() const { return TCF(red); }
   __device__ __forceinline__ uint64_t* bar_ready(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + s; }

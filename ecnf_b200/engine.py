@@ -242,9 +242,34 @@ class Engine:
                                              _ptr(ws), ws.numel(), _stream_ptr()), "ecnf_vf_forward_div")
         return out, div
 
+    def apply_hutchinson(self, params, x, t, eps, feat=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(f, eps^T J eps): the reference's approx=True divergence (sample_and_log_prob.py:69-78) with the probe eps [B, D]."""
+        packed = self.pack(params)
+        self._bind(packed)
+        x, feat, B = self._prep(x, feat)
+        t = torch.as_tensor(t, dtype=torch.float32, device=self.device).reshape(-1).contiguous()
+        eps = torch.as_tensor(eps, dtype=torch.float32, device=self.device).reshape(-1, self.cfg.D).contiguous()
+        if t.numel() != B or eps.shape[0] != B:
+            raise L.EcnfError(f"t and eps must have {B} rows, got {t.numel()} and {eps.shape[0]}")
+        out = torch.empty_like(x)
+        div = torch.empty(B, dtype=torch.float32, device=self.device)
+        nb = int(self.lib.ecnf_solve_workspace_bytes(self.handle, L.MODE_VF_DIV, B))
+        ws = self._workspace("solve", nb)
+        L.check(self.lib.ecnf_vf_forward_hutchinson(self.handle, _ptr(x), _ptr(t), _ptr(feat), _ptr(eps), B, _ptr(out),
+                                                    _ptr(div), _ptr(ws), ws.numel(), _stream_ptr()),
+                "ecnf_vf_forward_hutchinson")
+        return out, div
+
+    def normal_noise(self, key, n: int, global_offset: int = 0, substream: int = 1) -> torch.Tensor:
+        """N(0,1) [n, D] keyed by (key, global sample index, substream); substream 0 = the noise under base_sample(key)."""
+        out = torch.empty(n, self.cfg.D, dtype=torch.float32, device=self.device)
+        L.check(self.lib.ecnf_normal_noise(self.handle, C.c_uint64(key_to_seed(key)), global_offset, n, substream, _ptr(out),
+                                           _stream_ptr()), "ecnf_normal_noise")
+        return out
+
     # ---------------------------------------------------------------- ODE solves
-    def solve(self, params, mode: int, x_init, feat=None, ctrl: Optional[L.SolveCtrl] = None):
-        """Returns (x_out [B, D], logs [B, 3] or None, stats int32 [B, 4])."""
+    def solve(self, params, mode: int, x_init, feat=None, ctrl: Optional[L.SolveCtrl] = None, eps=None):
+        """Returns (x_out [B, D], logs [B, 3] or None, stats int32 [B, 4]).  eps [B, D]: Hutchinson probes (approx=True)."""
         packed = self.pack(params)
         self._bind(packed)
         x_init, feat, B = self._prep(x_init, feat)
@@ -254,8 +279,13 @@ class Engine:
         stats = torch.empty(B, 4, dtype=torch.int32, device=self.device)
         nb = int(self.lib.ecnf_solve_workspace_bytes(self.handle, mode, B))
         ws = self._workspace("solve", nb)
-        L.check(self.lib.ecnf_solve(self.handle, mode, _ptr(x_init), _ptr(feat), B, C.byref(ctrl), _ptr(out_x),
-                                    _ptr(logs), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr()), "ecnf_solve")
+        if eps is not None:
+            eps = torch.as_tensor(eps, dtype=torch.float32, device=self.device).reshape(-1, self.cfg.D).contiguous()
+            if eps.shape[0] != B or mode == L.MODE_SAMPLE:
+                raise L.EcnfError("Hutchinson probes need one row per trajectory and a log-density mode")
+        L.check(self.lib.ecnf_solve_hutchinson(self.handle, mode, _ptr(x_init), _ptr(feat), _ptr(eps), B, C.byref(ctrl),
+                                               _ptr(out_x), _ptr(logs), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr()),
+                "ecnf_solve_hutchinson")
         return out_x, logs, stats
 
     # ---------------------------------------------------------------- base distribution

@@ -63,6 +63,9 @@ SIGNATURES = {
     "ecnf_vf_forward": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "ecnf_vf_forward_div": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _P]),
     "ecnf_solve": (C.c_int, [_P, C.c_int, _P, _P, _I64, C.POINTER(SolveCtrl), _P, _P, _P, _P, _I64, _P]),
+    "ecnf_solve_hutchinson": (C.c_int, [_P, C.c_int, _P, _P, _P, _I64, C.POINTER(SolveCtrl), _P, _P, _P, _P, _I64, _P]),
+    "ecnf_vf_forward_hutchinson": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _I64, _P]),
+    "ecnf_normal_noise": (C.c_int, [_P, _U64, _I64, _I64, C.c_uint32, _P, _P]),
     "ecnf_base_sample": (C.c_int, [_P, _U64, _I64, _I64, _P, _P]),
     "ecnf_base_sample_from_noise": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ecnf_base_log_prob": (C.c_int, [_P, _P, _I64, _P, _P]),

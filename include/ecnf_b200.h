@@ -90,6 +90,11 @@ int ecnf_vf_forward(const ecnf_model* m, const float* x, const float* t, const i
  * with forward-mode tangents fused into the layer kernel instead of the reference's D reverse passes.      */
 int ecnf_vf_forward_div(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, int64_t B,
                         float* out_f, float* out_div, void* ws, int64_t ws_bytes, void* stream);
+/* Hutchinson estimate eps^T (df/dx) eps of the divergence with one caller-supplied probe eps [B, n_frames*dim] per
+ * sample: the reference's `approx=True` branch (sample_and_log_prob.py:69-78, :123-133).  One forward-mode tangent
+ * instead of n_frames*dim.                                                                                       */
+int ecnf_vf_forward_hutchinson(const ecnf_model* m, const float* x, const float* t, const int32_t* feat, const float* eps,
+                               int64_t B, float* out_f, float* out_div, void* ws, int64_t ws_bytes, void* stream);
 
 /* ---- ODE solve: diffrax.diffeqsolve(ODETerm, Dopri5, PIDController | ConstantStepSize) as one persistent
  * on-device loop per trajectory (call sites sample_and_log_prob.py:33-37,85-89,140-144).                   */
@@ -109,12 +114,22 @@ typedef struct ecnf_solve_ctrl {
 int ecnf_solve(const ecnf_model* m, int mode, const float* x_init, const int32_t* feat, int64_t B,
                const ecnf_solve_ctrl* ctrl, float* out_x, float* out_logs, int32_t* out_stats, void* ws,
                int64_t ws_bytes, void* stream);
+/* ecnf_solve with the Hutchinson estimate in place of the exact trace (modes SAMPLE_LOGQ / LOGPROB); the probe of a
+ * trajectory is fixed for the whole solve, as in the reference (eps == NULL: identical to ecnf_solve).           */
+int ecnf_solve_hutchinson(const ecnf_model* m, int mode, const float* x_init, const int32_t* feat, const float* eps,
+                          int64_t B, const ecnf_solve_ctrl* ctrl, float* out_x, float* out_logs, int32_t* out_stats,
+                          void* ws, int64_t ws_bytes, void* stream);
 
 /* ---- base distribution (build_cnf.py:46-61, zero_com_base.py:44-47,64-93)                                */
 /* x0 = base_scale * remove_mean(eps); eps from a counter-based Philox4x32-10 stream keyed by
  * (seed, global sample index) so a sharded run reproduces the single-GPU draw.                             */
 int ecnf_base_sample(const ecnf_model* m, uint64_t seed, int64_t global_offset, int64_t B, float* out_x0,
                      void* stream);
+/* N(0,1) draws [B, n_frames*dim] from the same counter-based stream as ecnf_base_sample: value = f(seed, global sample
+ * index goff + b, element, substream).  substream 0 reproduces the raw noise underneath ecnf_base_sample (the reference
+ * reuses the base-sample key for the Hutchinson probe, sample_and_log_prob.py:130,137); use another for independent
+ * draws (jax.random.normal(key, x.shape) in get_log_prob, sample_and_log_prob.py:55).                              */
+int ecnf_normal_noise(const ecnf_model* m, uint64_t seed, int64_t goff, int64_t B, uint32_t substream, float* out, void* stream);
 int ecnf_base_sample_from_noise(const ecnf_model* m, const float* eps, int64_t B, float* out_x0, void* stream);
 int ecnf_base_log_prob(const ecnf_model* m, const float* x, int64_t B, float* out, void* stream);
 

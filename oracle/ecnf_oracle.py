@@ -243,6 +243,16 @@ def vf_and_exact_div(p, cfg: CnfConfig, x: torch.Tensor, t: torch.Tensor, feat: 
     return f.detach(), div
 
 
+def vf_and_hutchinson_div(p, cfg: CnfConfig, x: torch.Tensor, t: torch.Tensor, feat: torch.Tensor, eps: torch.Tensor):
+    """(f, eps^T J eps): the Hutchinson estimate of tr df/dx with ONE fixed probe per trajectory, in reverse mode exactly
+    like the reference's ``approx`` branch: ``(eps_dfdy,) = vjp_fn(eps); approx_div = sum(eps_dfdy * eps)``
+    (sample_and_log_prob.py:69-78, :123-133).  The CUDA kernel computes the same scalar in forward mode (eps . J eps)."""
+    xg = x.detach().clone().requires_grad_(True)
+    f = egnn_apply(p, cfg, xg, t, feat)
+    (eps_dfdy,) = torch.autograd.grad(f, xg, grad_outputs=eps.to(f.dtype))
+    return f.detach(), (eps_dfdy * eps.to(f.dtype)).sum(dim=1)
+
+
 # --------------------------------------------------------------------------------------------------
 # base distribution, OT path, flow-matching loss, optimiser, ESS
 # --------------------------------------------------------------------------------------------------
@@ -505,26 +515,31 @@ def sample_cnf(p, cfg: CnfConfig, x0: torch.Tensor, feat: torch.Tensor, ctrl: So
     return dopri5(func, x0, 0.0, 1.0, ctrl)
 
 
-def _joint(p, cfg, feat):
+def _joint(p, cfg, feat, eps=None):
+    """exact trace (eps is None) or the Hutchinson estimate with the fixed per-trajectory probe ``eps`` [B, D]"""
     def func(t, y):
-        fx, div = vf_and_exact_div(p, cfg, y[:, :-1], t, feat)
+        if eps is None:
+            fx, div = vf_and_exact_div(p, cfg, y[:, :-1], t, feat)
+        else:
+            fx, div = vf_and_hutchinson_div(p, cfg, y[:, :-1], t, feat, eps)
         return torch.cat([fx, div[:, None]], dim=1)
     return func
 
 
-def sample_and_log_prob_cnf(p, cfg: CnfConfig, x0: torch.Tensor, feat: torch.Tensor, ctrl: SolveControl):
-    """sample_and_log_prob.py:97-149, exact branch; fixed-step uses the evident intent y0=(x0, 0)
-    (the reference passes y0=x0 there and cannot run, SURVEY Appendix C#2)."""
+def sample_and_log_prob_cnf(p, cfg: CnfConfig, x0: torch.Tensor, feat: torch.Tensor, ctrl: SolveControl, eps=None):
+    """sample_and_log_prob.py:97-149; ``eps`` = None: exact branch, else the ``approx`` (Hutchinson) branch with that
+    probe.  Fixed-step uses the evident intent y0=(x0, 0) (the reference passes y0=x0 there and cannot run, SURVEY
+    Appendix C#2)."""
     y0 = torch.cat([x0, torch.zeros(x0.shape[0], 1, dtype=x0.dtype)], dim=1)
-    y1, st = dopri5(_joint(p, cfg, feat), y0, 0.0, 1.0, ctrl)
+    y1, st = dopri5(_joint(p, cfg, feat, eps), y0, 0.0, 1.0, ctrl)
     log_q = base_log_prob(cfg, x0) - y1[:, -1]
     return y1[:, :-1], log_q, st
 
 
-def get_log_prob(p, cfg: CnfConfig, x: torch.Tensor, feat: torch.Tensor, ctrl: SolveControl):
-    """sample_and_log_prob.py:41-94, exact branch: t 1 -> 0; returns (log_p, log_prob_base, delta)."""
+def get_log_prob(p, cfg: CnfConfig, x: torch.Tensor, feat: torch.Tensor, ctrl: SolveControl, eps=None):
+    """sample_and_log_prob.py:41-94 (``eps``: see sample_and_log_prob_cnf): t 1 -> 0; returns (log_p, log_prob_base, delta)."""
     y0 = torch.cat([x, torch.zeros(x.shape[0], 1, dtype=x.dtype)], dim=1)
-    y1, st = dopri5(_joint(p, cfg, feat), y0, 1.0, 0.0, ctrl)
+    y1, st = dopri5(_joint(p, cfg, feat, eps), y0, 1.0, 0.0, ctrl)
     lpb = base_log_prob(cfg, y1[:, :-1])
     delta = y1[:, -1]
     return lpb + delta, lpb, delta, st

@@ -203,3 +203,25 @@ def test_oracle_fp32_reproduces_golden_fp64(name):
     loss, grads = O.fm_loss_and_grad(flat, cfg, torch.tensor(g["x_data"]), torch.tensor(g["x0"]), torch.tensor(g["t"]), feat)
     assert abs(float(loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
     assert np.abs(grads["EGNN_0/0/phi_e/Dense_1/kernel"].numpy() - g["grad_phi_e"]).max() < 1e-4 * np.abs(g["grad_phi_e"]).max()
+
+
+def test_hutchinson_estimator_is_unbiased_and_matches_jvp():
+    """approx branch (sample_and_log_prob.py:69-78): eps^T J eps from one reverse pass equals eps . (J eps) by finite
+    differences, and its mean over probes is the exact trace."""
+    cfg = O.CnfConfig(n_frames=4, dim=2, n_blocks_egnn=2, mlp_units=(64, 64), n_invariant_feat_hidden=32)
+    flat = O.init_params(cfg, seed=0, head_variance=1.0, bias_std=0.1)
+    p = O.to_torch(flat, torch.float64)
+    rng = np.random.default_rng(0)
+    x = torch.tensor(rng.standard_normal((1, 8)))
+    t = torch.tensor([0.3], dtype=torch.float64)
+    feat = torch.zeros(1, 4, dtype=torch.long)
+    _, div = O.vf_and_exact_div(p, cfg, x, t, feat)
+    eps = torch.tensor(rng.standard_normal((1, 8)))
+    _, h = O.vf_and_hutchinson_div(p, cfg, x, t, feat, eps)
+    d = 1e-6
+    jv = (O.egnn_apply(p, cfg, x + d * eps, t, feat) - O.egnn_apply(p, cfg, x - d * eps, t, feat)) / (2 * d)
+    assert abs(float((jv * eps).sum()) - float(h)) < 1e-6 * (abs(float(h)) + 1)
+    K = 3000
+    xs, ts, fs = x.expand(K, 8), t.expand(K), feat.expand(K, 4)
+    _, hs = O.vf_and_hutchinson_div(p, cfg, xs, ts, fs, torch.tensor(rng.standard_normal((K, 8))))
+    assert abs(float(hs.mean()) - float(div)) < 4 * float(hs.std()) / np.sqrt(K)
