@@ -123,3 +123,24 @@ def test_max_steps_status(cuda_device):
     _, _, stats = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, L.make_ctrl(max_steps=3))
     st = stats.cpu().numpy()
     assert (st[:, 3] == 1).all() and (st[:, 0] == 3).all()
+
+
+@pytest.mark.parametrize("case", ["dw4", "lj13"])
+def test_tensor_core_engine_is_deterministic_and_agrees_with_simt(case, cuda_device):
+    """The tcgen05 engine has no atomics in its data path: two launches (trajectories land on different CTAs through the
+    work queue) give bit-identical results, and they agree with the fp32 SIMT engine within the 3-pass bf16 error."""
+    B = 300 if case == "dw4" else 160
+    ocfg, flat, tree, eng, x0, feat = _setup(case, B, seed=21)
+    ctrl = L.make_ctrl(use_fixed_step_size=True, step_size=0.25)
+    try:
+        eng.lib.ecnf_set_engine(0)
+        a = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, ctrl)
+        b = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, ctrl)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        eng.lib.ecnf_set_engine(1)
+        c = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, ctrl)
+    finally:
+        eng.lib.ecnf_set_engine(0)
+    assert rel_err(a[0].cpu().numpy(), c[0].cpu().numpy()) < TOL
+    la, lc = a[1].cpu().numpy()[:, 0], c[1].cpu().numpy()[:, 0]
+    assert np.abs(la - lc).max() < TOL * (np.abs(lc).max() + 1)
