@@ -246,8 +246,17 @@ __global__ void colsum_kernel(const float* __restrict__ Z, int M, int N, float* 
   __shared__ float red[NTHREADS];
   const int tid = threadIdx.x, col = tid % N, lane_r = tid / N, nr = NTHREADS / N;
   const int m0 = blockIdx.x * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
-  float s = 0.f;
-  for (int r = m0 + lane_r; r < m1; r += nr) s += Z[(size_t)r * N + col];
+  // four independent partial sums keep four loads in flight per thread (the kernel is HBM bound)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = m0 + lane_r;
+  for (; r + 3 * nr < m1; r += 4 * nr) {
+    s0 += Z[(size_t)r * N + col];
+    s1 += Z[(size_t)(r + nr) * N + col];
+    s2 += Z[(size_t)(r + 2 * nr) * N + col];
+    s3 += Z[(size_t)(r + 3 * nr) * N + col];
+  }
+  for (; r < m1; r += nr) s0 += Z[(size_t)r * N + col];
+  float s = (s0 + s1) + (s2 + s3);
   red[tid] = s;
   __syncthreads();
   if (lane_r == 0) {
@@ -795,7 +804,7 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   int cur = 0;        // dxs[cur] = grad wrt coordinates leaving block b
   int hcur = 0;       // dh[hcur] = grad wrt h leaving block b (valid for b < nb-1)
   auto colsum = [&](const float* Z, size_t M, int N, const float* out) {
-    const int rows = 2048;
+    const int rows = 256;     // >= 4 CTAs per SM for the big (edge-row) matrices
     colsum_kernel<<<(unsigned)((M + rows - 1) / rows), NTHREADS, 0, st>>>(Z, (int)M, N, const_cast<float*>(out), rows);
   };
   for (int b = nb - 1; b >= 0; --b) {
