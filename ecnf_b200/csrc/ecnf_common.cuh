@@ -52,6 +52,7 @@ struct ecnf_model {
 
 EcnfModelDev ecnf_make_dev(const ecnf_model* m, const float* d_params);
 void ecnf_set_error(const char* fmt, ...);
+int ecnf_engine_choice();   // ecnf_set_engine: 0 = tensor cores where eligible, 1 = fp32 SIMT everywhere
 
 #define ECNF_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \

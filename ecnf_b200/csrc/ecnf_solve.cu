@@ -79,6 +79,8 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
 
 }  // namespace
 
+int ecnf_engine_choice() { return g_engine; }
+
 extern "C" {
 
 int64_t ecnf_solve_workspace_bytes(const ecnf_model* m, int mode, int64_t B) {

@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "ecnf_tile.cuh"
+#include "ecnf_train_tc.cuh"
 
 namespace {
 using ecnf_tile::ColT;
@@ -120,6 +121,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_rows_kernel(const __grid_con
 
 template <int K, int N, int K2>
 int launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t st) {
+  // the big square edge-row GEMMs go to the tensor cores (ecnf_train_tc.cuh) unless the SIMT engine is forced
+  if constexpr (K == N && (K == 128 || K == 256)) {
+    if (!g.A2 && g.M >= 8192 && ecnf_engine_choice() == 0) {
+      ecnf_train_tc::Args a{g.A, g.W, g.bias, g.rowvec, g.rows_per_vec, g.resid, g.add, g.mulz, g.C, g.M, g.a_op};
+      ECNF_CHECK_CUDA((ecnf_train_tc::launch<K, N>(a, num_sms, st)));
+      return ECNF_OK;
+    }
+  }
   constexpr int TR = GemmGeo<K, N>::TR;
   const size_t smem = (size_t)(TR * (K + 4) + (K2 > 0 ? TR * (K2 + 4) : 0) + 2 * WCHUNK) * sizeof(float);
   auto kern = gemm_rows_kernel<K, N, K2>;

@@ -114,3 +114,40 @@ def test_update_fn_three_steps_match_oracle(cuda_device):
         # Adam's first steps move every weight by ~lr regardless of gradient size: compare absolutely
         assert np.abs(node - p_ref[k]).max() < 2e-5, k
     assert state.opt_state.count == 3
+
+
+@pytest.mark.parametrize("case,B", [("qm9_like", 220), ("lj13", 60)])
+def test_tensor_core_gemms_match_simt_and_autograd(case, B, cuda_device):
+    """Batches whose edge-row count (>= 8192) sends the square Dense GEMMs (forward and backward-data) to the tcgen05
+    kernel (ecnf_train_tc.cuh): loss / gradient agree with the fp32 SIMT path and, on a subset, with fp64 autograd."""
+    n, dim, blocks, units, H, nfeat = CASES[case]
+    assert B * n * (n - 1) >= 8192
+    ocfg, flat, tree, ecfg = make_pair(n, dim, blocks, units, H, n_features=nfeat)
+    eng = Engine(ecfg)
+    x_data, x0, t, feat = _batch(ocfg, B, nfeat, 13)
+    try:
+        eng.lib.ecnf_set_engine(0)
+        loss_tc, grad_tc = eng.fm_loss_grad(tree, x_data, x0, t, feat.int())
+        loss_tc, grad_tc = float(loss_tc[0]), grad_tc.clone()
+        eng.lib.ecnf_set_engine(1)
+        loss_s, grad_s = eng.fm_loss_grad(tree, x_data, x0, t, feat.int())
+        loss_s, grad_s = float(loss_s[0]), grad_s.clone()
+    finally:
+        eng.lib.ecnf_set_engine(0)
+    assert abs(loss_tc - loss_s) < LOSS_TOL * abs(loss_s)
+    assert not torch.equal(grad_tc, grad_s)          # the two paths really differ in arithmetic
+    gt = eng.unpack(grad_tc, to_numpy=True)["params"]
+    gs = eng.unpack(grad_s, to_numpy=True)["params"]
+    loss_ref, g_ref = O.fm_loss_and_grad(flat, ocfg, x_data, x0, t, feat, dtype=torch.float64)
+    assert abs(loss_tc - float(loss_ref)) < LOSS_TOL * abs(float(loss_ref))
+    for path, _ in O.param_layout(ocfg):
+        a, b = gt, gs
+        for part in path.split("/"):
+            a, b = a[part], b[part]
+        ref = g_ref[path].numpy()
+        scale = np.abs(ref).max() + 1e-12
+        if np.abs(ref).max() == 0.0:
+            assert np.abs(a).max() == 0.0, path
+            continue
+        assert np.abs(a - b).max() / scale < GRAD_TOL, (path, "tc vs simt")
+        assert np.abs(a - ref).max() / scale < GRAD_TOL, (path, "tc vs autograd")
