@@ -229,6 +229,12 @@ __global__ void __launch_bounds__(NTHREADS) dw_kernel(const float* __restrict__ 
 
 int launch_dw(const float* A, int lda, int a_op, const float* dZ, int ldz, float* dW, int K, int N, int M, int num_sms,
               cudaStream_t st) {
+  // the big square weight gradients (reduction over the edge rows) go to the tensor cores (ecnf_train_tc.cuh)
+  if (lda == K && ldz == N && K == N && (K == 128 || K == 256) && M >= 8192 && ecnf_engine_choice() == 0) {
+    if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, M, num_sms, st)));
+    else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, M, num_sms, st)));
+    return ECNF_OK;
+  }
   // block shape: 128 where the dimension allows, else 64 / 32
   auto pick = [](int d) { return d % 128 == 0 ? 128 : (d % 64 == 0 ? 64 : 32); };
   const int BK = pick(K), BN = pick(N);

@@ -210,4 +210,141 @@ cudaError_t launch(const Args& g, int num_sms, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// =====================================================================================================================
+// dW[K, N] += op(A)[M, K]^T dZ[M, N]   (weight gradients: the reduction runs over the M = 175 k edge rows)
+//
+//   D[k (TMEM lane), n (column)] += A'[k][m] B'[m][n]  with K' = m: both operands are the row-major fp32 matrices
+//   themselves, which is exactly the MN-major canonical layout once 8 consecutive columns of a row are packed into one
+//   16-byte bf16 vector:  offset(col, m) = (m/8) LBO + (col/8) 128 + (m%8) 16 + (col%8) 2.  A CTA walks its slab of rows
+//   in 32-row chunks: coalesced loads -> op -> bf16 (hi, lo) -> shared memory (conflict-free 512-byte warp stores), two
+//   stages, the MMAs of chunk c (3 passes x 2 row steps x K/128 lane halves, N = 256 columns each) run while chunk c+1 is
+//   converted.  The fp32 accumulators fill tensor memory (K/128 x N columns); at the end every CTA adds its partial to
+//   dW with 16-byte vector reductions.
+// =====================================================================================================================
+constexpr uint32_t IDESC_A_MN = 1u << 15;
+
+template <int C>   // convert rows [r0, r0 + 32) of a row-major [M x C] matrix into the (hi, lo) images at dst (C * 64 B each)
+__device__ __forceinline__ void convert_chunk(const float* __restrict__ src, int M, int r0, int op, unsigned char* dst_hi,
+                                              unsigned char* dst_lo, int tid) {
+  constexpr int XB = C / 32;                  // blocks of 4 column groups (32 columns) per row
+  constexpr int NJ = 4 * XB / 8;              // (row group, block) combinations per warp
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int combo = warp + 8 * j, mg = combo & 3, x = combo >> 2;
+    const int m = 8 * mg + (lane & 7), cg = 4 * x + (lane >> 3);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (r0 + m < M) {
+      const float* p = src + (size_t)(r0 + m) * C + 8 * cg;
+      a = *reinterpret_cast<const float4*>(p);
+      b = *reinterpret_cast<const float4*>(p + 4);
+    }
+    if (op) {
+      a.x = silu(a.x); a.y = silu(a.y); a.z = silu(a.z); a.w = silu(a.w);
+      b.x = silu(b.x); b.y = silu(b.y); b.z = silu(b.z); b.w = silu(b.w);
+    }
+    uint32_t h[4], l[4];
+    split_pack(a.x, a.y, h[0], l[0]); split_pack(a.z, a.w, h[1], l[1]);
+    split_pack(b.x, b.y, h[2], l[2]); split_pack(b.z, b.w, h[3], l[3]);
+    const int off = mg * (C * 16) + cg * 128 + (m & 7) * 16;
+    *reinterpret_cast<uint4*>(dst_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dst_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+template <int K, int N>
+__global__ void __launch_bounds__(256, 1) dw_tc_kernel(const float* __restrict__ A, int a_op, const float* __restrict__ dZ,
+                                                       float* __restrict__ dW, int M, int rows_per_cta) {
+  static_assert((K == 128 || K == 256) && (N == 128 || N == 256) && (K / 128) * N <= 512, "shapes");
+  constexpr int A_IMG = 32 * K * 2, B_IMG = 32 * N * 2;           // bytes of one (hi or lo) image of a 32-row chunk
+  constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int m_begin = blockIdx.x * rows_per_cta, m_end = min(M, m_begin + rows_per_cta);
+  const int nchunks = (m_end - m_begin + 31) / 32;
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1;
+    if (c >= 2) { mbar_wait(&bar[s], ((c >> 1) - 1) & 1); tc_fence_after(); }     // the MMAs of chunk c-2 have left stage s
+    unsigned char* st = smem + s * STAGE;
+    convert_chunk<K>(A, m_end, m_begin + 32 * c, a_op, st, st + A_IMG, tid);
+    convert_chunk<N>(dZ, m_end, m_begin + 32 * c, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_A_MN | IDESC_B_MN;
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
+      constexpr uint32_t LBO_A = K * 16, LBO_B = N * 16;
+#pragma unroll
+      for (int h = 0; h < K / 128; ++h) {
+#pragma unroll
+        for (int ms = 0; ms < 2; ++ms) {
+          const uint64_t ah = make_sdesc(a_hi + h * 2048 + ms * 2 * LBO_A, LBO_A, 128);
+          const uint64_t al = make_sdesc(a_lo + h * 2048 + ms * 2 * LBO_A, LBO_A, 128);
+          const uint64_t bh = make_sdesc(b_hi + ms * 2 * LBO_B, LBO_B, 128);
+          const uint64_t bl = make_sdesc(b_lo + ms * 2 * LBO_B, LBO_B, 128);
+          const uint32_t acc = tmem + (uint32_t)(h * N);
+          mma_ss(acc, ah, bh, idesc, (c > 0 || ms > 0) ? 1u : 0u);
+          mma_ss(acc, al, bh, idesc, 1u);
+          mma_ss(acc, ah, bl, idesc, 1u);
+        }
+      }
+      mma_commit(&bar[s]);
+    }
+  }
+  // the last commit covers every MMA issued before it (they all come from thread 0)
+  if (nchunks > 0) {
+    const int c = nchunks - 1;
+    mbar_wait(&bar[c & 1], (c >> 1) & 1);
+    tc_fence_after();
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const int lane_k = tid & 127, ch = tid >> 7;          // my lane (k within the half) and my half of the N columns
+#pragma unroll 1
+    for (int h = 0; h < K / 128; ++h) {
+#pragma unroll 1
+      for (int q = 0; q < N / 64; ++q) {
+        uint32_t v[32];
+        const int col = ch * (N / 2) + 32 * q;
+        tmem_ld32(tmem + (uint32_t)(h * N) + lane_addr + (uint32_t)col, v);
+        tmem_wait_ld();
+        float* dst = dW + (size_t)(128 * h + lane_k) * N + col;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c4), "f"(__uint_as_float(v[4 * c4])),
+                       "f"(__uint_as_float(v[4 * c4 + 1])), "f"(__uint_as_float(v[4 * c4 + 2])), "f"(__uint_as_float(v[4 * c4 + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int K, int N>
+cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, int M, int num_sms, cudaStream_t st) {
+  constexpr int STAGE = 2 * (32 * K * 2) + 2 * (32 * N * 2);
+  const size_t smem = 2 * STAGE;
+  auto kern = dw_tc_kernel<K, N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int rows_per_cta = ((M + num_sms - 1) / num_sms + 31) / 32 * 32;
+  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  kern<<<grid, 256, smem, st>>>(A, a_op, dZ, dW, M, rows_per_cta);
+  return cudaGetLastError();
+}
+
 }  // namespace ecnf_train_tc
