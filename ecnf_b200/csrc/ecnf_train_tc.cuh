@@ -235,16 +235,19 @@ cudaError_t launch(const Args& g, int num_sms, cudaStream_t st) {
 //   dW with 16-byte vector reductions.
 // =====================================================================================================================
 constexpr uint32_t IDESC_A_MN = 1u << 15;
+constexpr int DW_NT = 512;
 
 template <int C>   // convert rows [r0, r0 + 32) of a row-major [M x C] matrix into the (hi, lo) images at dst (C * 64 B each)
 __device__ __forceinline__ void convert_chunk(const float* __restrict__ src, int M, int r0, int op, unsigned char* dst_hi,
                                               unsigned char* dst_lo, int tid) {
   constexpr int XB = C / 32;                  // blocks of 4 column groups (32 columns) per row
-  constexpr int NJ = 4 * XB / 8;              // (row group, block) combinations per warp
+  constexpr int NW = DW_NT / 32;
+  constexpr int NJ = 4 * XB / NW;             // (row group, block) combinations per warp
+  static_assert(NJ >= 1, "warps");
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const int combo = warp + 8 * j, mg = combo & 3, x = combo >> 2;
+    const int combo = warp + NW * j, mg = combo & 3, x = combo >> 2;
     const int m = 8 * mg + (lane & 7), cg = 4 * x + (lane >> 3);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (r0 + m < M) {
@@ -266,7 +269,7 @@ __device__ __forceinline__ void convert_chunk(const float* __restrict__ src, int
 }
 
 template <int K, int N>
-__global__ void __launch_bounds__(256, 1) dw_tc_kernel(const float* __restrict__ A, int a_op, const float* __restrict__ dZ,
+__global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict__ A, int a_op, const float* __restrict__ dZ,
                                                        float* __restrict__ dW, int M, int rows_per_cta) {
   static_assert((K == 128 || K == 256) && (N == 128 || N == 256) && (K / 128) * N <= 512, "shapes");
   constexpr int A_IMG = 32 * K * 2, B_IMG = 32 * N * 2;           // bytes of one (hi or lo) image of a 32-row chunk
@@ -320,13 +323,13 @@ __global__ void __launch_bounds__(256, 1) dw_tc_kernel(const float* __restrict__
     mbar_wait(&bar[c & 1], (c >> 1) & 1);
     tc_fence_after();
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    const int lane_k = tid & 127, ch = tid >> 7;          // my lane (k within the half) and my half of the N columns
+    const int lane_k = tid & 127, ch = tid >> 7;          // my lane (k within the half) and my quarter of the N columns
 #pragma unroll 1
     for (int h = 0; h < K / 128; ++h) {
 #pragma unroll 1
-      for (int q = 0; q < N / 64; ++q) {
+      for (int q = 0; q < N / 128; ++q) {
         uint32_t v[32];
-        const int col = ch * (N / 2) + 32 * q;
+        const int col = ch * (N / 4) + 32 * q;
         tmem_ld32(tmem + (uint32_t)(h * N) + lane_addr + (uint32_t)col, v);
         tmem_wait_ld();
         float* dst = dW + (size_t)(128 * h + lane_k) * N + col;
@@ -356,7 +359,7 @@ cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, int 
   }
   int rows_per_cta = ((M + num_sms - 1) / num_sms + 31) / 32 * 32;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, 256, smem, st>>>(A, a_op, dZ, dW, M, rows_per_cta);
+  kern<<<grid, DW_NT, smem, st>>>(A, a_op, dZ, dW, M, rows_per_cta);
   return cudaGetLastError();
 }
 
