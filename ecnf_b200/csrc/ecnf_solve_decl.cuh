@@ -7,7 +7,7 @@ namespace ecnf_solve_detail {
 // per-CTA global scratch (floats): h (current), h_in, P_s, P_r, aggregated messages, P_h (tensor-core engine only)
 __host__ __device__ inline int64_t scratch_floats(int n, int dim, int H, int U, bool div) {
   const int64_t ND = div ? 1 + n * dim : 1;
-  return n * ND * (2 * (int64_t)H + 4 * (int64_t)U);
+  return n * ND * (2 * (int64_t)H + 4 * (int64_t)U) + 2 * (int64_t)U;   // + one all-zero row after P_s and after P_r (tensor-core engine)
 }
 
 // byte offsets of the bf16 (hi, lo) weight images used by the tensor-core engine (ecnf_solve_tc.cuh)

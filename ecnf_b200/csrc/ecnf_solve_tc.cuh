@@ -238,8 +238,9 @@ struct EngineTC {
   __device__ __forceinline__ float* hA() const { return a.scratch + (size_t)blockIdx.x * a.scratch_stride; }
   __device__ __forceinline__ float* hB() const { return hA() + (size_t)n * ND * H; }
   __device__ __forceinline__ float* Ps() const { return hB() + (size_t)n * ND * H; }
-  __device__ __forceinline__ float* Pr() const { return Ps() + (size_t)n * ND * U; }
-  __device__ __forceinline__ float* Mg() const { return Pr() + (size_t)n * ND * U; }
+  // P_s and P_r carry one extra, all-zero row (index n * ND): the gather of phi_e layer 0 points there for rows without a P part
+  __device__ __forceinline__ float* Pr() const { return Ps() + ((size_t)n * ND + 1) * U; }
+  __device__ __forceinline__ float* Mg() const { return Pr() + ((size_t)n * ND + 1) * U; }
   __device__ __forceinline__ float* Ph() const { return Mg() + (size_t)n * ND * U; }
 
   __device__ __forceinline__ EngineTC(const KernelArgs& a_)
@@ -268,6 +269,7 @@ struct EngineTC {
 #pragma unroll
       for (int q = 0; q < 4; ++q) tmem_st32(tmem + lane_addr + 128u * hh + 32u * q, z);
       tmem_wait_st();
+      (hh ? Pr() : Ps())[(size_t)n * ND * U + f] = 0.f;      // the zero rows of P_s / P_r
     }
     tc_fence_before();
     __syncthreads();
@@ -730,7 +732,7 @@ struct EngineTC {
       if (e.tid < 128) {
         const uint32_t w = __ldg(tp + e.tid);
         const int win = (int)__ldg(tp + 192 + TH_WIN);
-        int oS = -1, oR = 0, mr = a.lay.mrows * TCU, ijk = 0;
+        int oS = n * ND * TCU, oR = n * ND * TCU, mr = a.lay.mrows * TCU, ijk = 0;     // default: the zero rows
         float sd = 0.f;
         if (w & CW_VALID) {
           const int ed = cw_gid(w), q = cw_q(w);
@@ -773,20 +775,14 @@ struct EngineTC {
 #pragma unroll
       for (int cb = 0; cb < 64; cb += 16) {
         float pa[16], pb[16];
-        int os[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int col = s * 128 + 64 * e.hh + cb + u;
-          os[u] = TCI(coloffS)[col];
-          const int orr = TCI(coloffR)[col];
-          pa[u] = ps[os[u] >= 0 ? os[u] : 0];
-          pb[u] = pr[orr];
+          pa[u] = ps[TCI(coloffS)[col]];
+          pb[u] = pr[TCI(coloffR)[col]];
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const float sd = TCF(colsd)[s * 128 + 64 * e.hh + cb + u];
-          v[cb + u] = os[u] >= 0 ? fmaf(sd, wdf, pa[u] + pb[u]) : sd * wdf;
-        }
+        for (int u = 0; u < 16; ++u) v[cb + u] = fmaf(TCF(colsd)[s * 128 + 64 * e.hh + cb + u], wdf, pa[u] + pb[u]);
       }
       e.qend(P_GATHER);
       e.act_rule(v, 0.f, s);
