@@ -227,13 +227,20 @@ __global__ void __launch_bounds__(NTHREADS) dw_kernel(const float* __restrict__ 
     }
 }
 
+__global__ void colsum_kernel(const float* __restrict__ Z, int M, int N, float* __restrict__ out, int rows_per_cta);
+
+// dW += op(A)^T dZ; bias_grad (optional) += column sums of dZ (fused into the tensor-core kernel, else a second launch)
 int launch_dw(const float* A, int lda, int a_op, const float* dZ, int ldz, float* dW, int K, int N, int M, int num_sms,
-              cudaStream_t st) {
+              cudaStream_t st, float* bias_grad = nullptr) {
   // the big square weight gradients (reduction over the edge rows) go to the tensor cores (ecnf_train_tc.cuh)
   if (lda == K && ldz == N && K == N && (K == 128 || K == 256) && M >= 8192 && ecnf_engine_choice() == 0) {
-    if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, M, num_sms, st)));
-    else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, M, num_sms, st)));
+    if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
+    else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
     return ECNF_OK;
+  }
+  if (bias_grad) {
+    const int rows = 256;
+    colsum_kernel<<<(unsigned)((M + rows - 1) / rows), NTHREADS, 0, st>>>(dZ, M, N, bias_grad, rows);
   }
   // block shape: 128 where the dimension allows, else 64 / 32
   auto pick = [](int d) { return d % 128 == 0 ? 128 : (d % 64 == 0 ? 64 : 32); };
@@ -859,8 +866,8 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
     // phi_x chain
     for (int l = L - 1; l >= 0; --l) {
       const float* Ain = (l == 0) ? Ze[b][L - 1] : Zx[b][l - 1];
-      if ((rc = launch_dw(Ain, U, 1, Zx[b][l], U, const_cast<float*>(gp.Wx[l]), U, U, (int)EB, sms, st))) return rc;
-      colsum(Zx[b][l], EB, U, gp.bx[l]);
+      if ((rc = launch_dw(Ain, U, 1, Zx[b][l], U, const_cast<float*>(gp.Wx[l]), U, U, (int)EB, sms, st,
+                          const_cast<float*>(gp.bx[l])))) return rc;
       GemmArgs g = gemm_args(Zx[b][l], q.Wx[l], l == 0 ? Ze[b][L - 1] : Zx[b][l - 1], (int)EB);
       g.mulz = (l == 0) ? Ze[b][L - 1] : Zx[b][l - 1];
       if (l == 0) g.add = DM;
@@ -868,8 +875,8 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
     }
     // phi_e chain
     for (int l = L - 1; l >= 1; --l) {
-      if ((rc = launch_dw(Ze[b][l - 1], U, 1, Ze[b][l], U, const_cast<float*>(gp.We[l]), U, U, (int)EB, sms, st))) return rc;
-      colsum(Ze[b][l], EB, U, gp.be[l]);
+      if ((rc = launch_dw(Ze[b][l - 1], U, 1, Ze[b][l], U, const_cast<float*>(gp.We[l]), U, U, (int)EB, sms, st,
+                          const_cast<float*>(gp.be[l])))) return rc;
       GemmArgs g = gemm_args(Ze[b][l], q.We[l], Ze[b][l - 1], (int)EB);
       g.mulz = Ze[b][l - 1];
       if ((rc = launch_gemm<U, U, H>(g, sms, st))) return rc;

@@ -237,9 +237,11 @@ cudaError_t launch(const Args& g, int num_sms, cudaStream_t st) {
 constexpr uint32_t IDESC_A_MN = 1u << 15;
 constexpr int DW_NT = 512;
 
-template <int C>   // convert rows [r0, r0 + 32) of a row-major [M x C] matrix into the (hi, lo) images at dst (C * 64 B each)
+// convert rows [r0, r0 + 32) of a row-major [M x C] matrix into the (hi, lo) images at dst (C * 64 B each); csum (optional)
+// accumulates this thread's share of the column sums (the bias gradient) on the way
+template <int C, bool SUM>
 __device__ __forceinline__ void convert_chunk(const float* __restrict__ src, int M, int r0, int op, unsigned char* dst_hi,
-                                              unsigned char* dst_lo, int tid) {
+                                              unsigned char* dst_lo, int tid, float (&csum)[4 * (C / 32) / (512 / 32)][8]) {
   constexpr int XB = C / 32;                  // blocks of 4 column groups (32 columns) per row
   constexpr int NW = DW_NT / 32;
   constexpr int NJ = 4 * XB / NW;             // (row group, block) combinations per warp
@@ -259,6 +261,10 @@ __device__ __forceinline__ void convert_chunk(const float* __restrict__ src, int
       a.x = silu(a.x); a.y = silu(a.y); a.z = silu(a.z); a.w = silu(a.w);
       b.x = silu(b.x); b.y = silu(b.y); b.z = silu(b.z); b.w = silu(b.w);
     }
+    if (SUM) {
+      csum[j][0] += a.x; csum[j][1] += a.y; csum[j][2] += a.z; csum[j][3] += a.w;
+      csum[j][4] += b.x; csum[j][5] += b.y; csum[j][6] += b.z; csum[j][7] += b.w;
+    }
     uint32_t h[4], l[4];
     split_pack(a.x, a.y, h[0], l[0]); split_pack(a.z, a.w, h[1], l[1]);
     split_pack(b.x, b.y, h[2], l[2]); split_pack(b.z, b.w, h[3], l[3]);
@@ -270,7 +276,8 @@ __device__ __forceinline__ void convert_chunk(const float* __restrict__ src, int
 
 template <int K, int N>
 __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict__ A, int a_op, const float* __restrict__ dZ,
-                                                       float* __restrict__ dW, int M, int rows_per_cta) {
+                                                       float* __restrict__ dW, float* __restrict__ colsum, int M,
+                                                       int rows_per_cta) {
   static_assert((K == 128 || K == 256) && (N == 128 || N == 256) && (K / 128) * N <= 512, "shapes");
   constexpr int A_IMG = 32 * K * 2, B_IMG = 32 * N * 2;           // bytes of one (hi or lo) image of a 32-row chunk
   constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;
@@ -286,12 +293,19 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
   const uint32_t tmem = tmem_slot;
   const int m_begin = blockIdx.x * rows_per_cta, m_end = min(M, m_begin + rows_per_cta);
   const int nchunks = (m_end - m_begin + 31) / 32;
+  constexpr int NJA = 4 * (K / 32) / (DW_NT / 32), NJB = 4 * (N / 32) / (DW_NT / 32);
+  float asum[NJA][8], bsum[NJB][8];      // asum is never used (SUM = false); bsum: column sums of dZ = the bias gradient
+#pragma unroll
+  for (int j = 0; j < NJB; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bsum[j][i] = 0.f;
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
     if (c >= 2) { mbar_wait(&bar[s], ((c >> 1) - 1) & 1); tc_fence_after(); }     // the MMAs of chunk c-2 have left stage s
     unsigned char* st = smem + s * STAGE;
-    convert_chunk<K>(A, m_end, m_begin + 32 * c, a_op, st, st + A_IMG, tid);
-    convert_chunk<N>(dZ, m_end, m_begin + 32 * c, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid);
+    convert_chunk<K, false>(A, m_end, m_begin + 32 * c, a_op, st, st + A_IMG, tid, asum);
+    if (colsum) convert_chunk<N, true>(dZ, m_end, m_begin + 32 * c, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
+    else convert_chunk<N, false>(dZ, m_end, m_begin + 32 * c, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -315,6 +329,22 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
         }
       }
       mma_commit(&bar[s]);
+    }
+  }
+  if (colsum) {
+    // my partial column sums: lanes that differ in the row (lane & 7) hold the same columns
+    const int lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < NJB; ++j) {
+      const int combo = warp + (DW_NT / 32) * j, x = combo >> 2, cg = 4 * x + (lane >> 3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = bsum[j][i];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if ((lane & 7) == 0) atomicAdd(colsum + 8 * cg + i, v);
+      }
     }
   }
   // the last commit covers every MMA issued before it (they all come from thread 0)
@@ -347,7 +377,7 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
 }
 
 template <int K, int N>
-cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, int M, int num_sms, cudaStream_t st) {
+cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, float* colsum, int M, int num_sms, cudaStream_t st) {
   constexpr int STAGE = 2 * (32 * K * 2) + 2 * (32 * N * 2);
   const size_t smem = 2 * STAGE;
   auto kern = dw_tc_kernel<K, N>;
@@ -359,7 +389,7 @@ cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, int 
   }
   int rows_per_cta = ((M + num_sms - 1) / num_sms + 31) / 32 * 32;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, DW_NT, smem, st>>>(A, a_op, dZ, dW, M, rows_per_cta);
+  kern<<<grid, DW_NT, smem, st>>>(A, a_op, dZ, dW, colsum, M, rows_per_cta);
   return cudaGetLastError();
 }
 
