@@ -477,72 +477,120 @@ __global__ void loss_kernel(Dims d, const float* __restrict__ xsL, const float* 
 // In:  dM [B*n, U] (grad wrt aggregated message, null in the last block), dxs_next [B, D]
 // Out: DM [EB, U] = grad wrt m from the message path (0 if last); Zx <- d z_x[L-1] (in place);
 //      dvgeo [EB, 4] = grad wrt v_ij from the coordinate path; accumulates d wa, d ba, d wp, d bp.
+// Lane l owns the VW = min(4, U/32) consecutive columns (32 v + l) VW .. of every group v < NV of 32 VW columns, so
+// every access is one 8- or 16-byte vector and a warp covers 32 VW contiguous floats; all loads of a row are issued before
+// the first use, and the elementwise SiLU uses ex2 / rcp (as in ecnf_train_tc.cuh).
+template <int VW> struct VecT;
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+template <int VW>
+__device__ __forceinline__ void ldv(const float* p, float (&o)[VW]) {
+  const typename VecT<VW>::T v = *reinterpret_cast<const typename VecT<VW>::T*>(p);
+  const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+  for (int i = 0; i < VW; ++i) o[i] = f[i];
+}
+template <int VW>
+__device__ __forceinline__ void stv(float* p, const float (&o)[VW]) {
+  typename VecT<VW>::T v;
+  float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+  for (int i = 0; i < VW; ++i) f[i] = o[i];
+  *reinterpret_cast<typename VecT<VW>::T*>(p) = v;
+}
+
 template <int U>
-__global__ void heads_bwd_kernel(Dims d, const float* __restrict__ xs, const float* __restrict__ Ze,
+__global__ void __launch_bounds__(256) heads_bwd_kernel(Dims d, const float* __restrict__ xs, const float* __restrict__ Ze,
                                  float* __restrict__ Zx, const float* __restrict__ eatt, const float* __restrict__ p,
                                  const float* __restrict__ dM, const float* __restrict__ dxs_next,
                                  const float* __restrict__ wa, const float* __restrict__ wp, float* __restrict__ DM,
                                  float* __restrict__ dvgeo, float* __restrict__ g_wa, float* __restrict__ g_ba,
                                  float* __restrict__ g_wp, float* __restrict__ g_bp, int rows_per_warp) {
-  constexpr int Q = U / 32;
+  constexpr int Q = U / 32, VW = Q < 4 ? Q : 4, NV = Q / VW;
+  using ecnf_train_tc::sigm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const size_t EB = (size_t)d.B * d.E;
   const size_t r_begin = ((size_t)blockIdx.x * nw + warp) * rows_per_warp;
   const size_t r_end = min(EB, r_begin + rows_per_warp);
-  float awa[Q], awp[Q], aba = 0.f, abp = 0.f, wav[Q], wpv[Q];
+  float awa[NV][VW], awp[NV][VW], aba = 0.f, abp = 0.f, wav[NV][VW], wpv[NV][VW];
 #pragma unroll
-  for (int q = 0; q < Q; ++q) { awa[q] = 0.f; awp[q] = 0.f; wav[q] = wa[lane + 32 * q]; wpv[q] = wp[lane + 32 * q]; }
+  for (int v = 0; v < NV; ++v) {
+    ldv<VW>(wa + (32 * v + lane) * VW, wav[v]);
+    ldv<VW>(wp + (32 * v + lane) * VW, wpv[v]);
+#pragma unroll
+    for (int i = 0; i < VW; ++i) { awa[v][i] = 0.f; awp[v][i] = 0.f; }
+  }
   const float inv_sqrt = rsqrtf((float)(d.n - 1)), inv_nb = 1.f / (float)(d.n - 1);
+#pragma unroll 2
   for (size_t row = r_begin; row < r_end; ++row) {
     const int g = (int)(row / d.E);
     int i, j;
     edge_nodes((int)(row - (size_t)g * d.E), d.n, i, j);
+    float ze[NV][VW], zx[NV][VW], dmr[NV][VW];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (32 * v + lane) * VW;
+      ldv<VW>(Ze + row * U + col, ze[v]);
+      ldv<VW>(Zx + row * U + col, zx[v]);
+      if (dM) ldv<VW>(dM + ((size_t)g * d.n + i) * U + col, dmr[v]);
+    }
     const float* xg = xs + (size_t)g * d.D;
-    float v[3] = {0.f, 0.f, 0.f}, s = 0.f, dcv = 0.f, dc[3] = {0.f, 0.f, 0.f};
+    float v3[3] = {0.f, 0.f, 0.f}, s = 0.f, dcv = 0.f, dc[3] = {0.f, 0.f, 0.f};
     for (int c = 0; c < d.dim; ++c) {
-      v[c] = xg[i * d.dim + c] - xg[j * d.dim + c];
-      s = fmaf(v[c], v[c], s);
+      v3[c] = xg[i * d.dim + c] - xg[j * d.dim + c];
+      s = fmaf(v3[c], v3[c], s);
       dc[c] = dxs_next[(size_t)g * d.D + i * d.dim + c] * inv_nb;
-      dcv = fmaf(dc[c], v[c], dcv);
+      dcv = fmaf(dc[c], v3[c], dcv);
     }
     const bool isz = (s == 0.f);
     const float len = sqrtf(isz ? 1.f : s), inv = 1.f / (d.C + len);
     const float pv = p[row], e = eatt[row];
     const float dp = dcv * inv;
-    float mreg[Q], de = 0.f;
+    float de = 0.f;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int col = lane + 32 * q;
-      mreg[q] = silu_f(Ze[row * U + col]);
-      if (dM) de = fmaf(dM[((size_t)g * d.n + i) * U + col] * inv_sqrt, mreg[q], de);
-    }
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < VW; ++k) {
+        ze[v][k] *= sigm(ze[v][k]);                       // m = silu(z_e)
+        if (dM) { dmr[v][k] *= inv_sqrt; de = fmaf(dmr[v][k], ze[v][k], de); }
+      }
     for (int o = 16; o > 0; o >>= 1) de += __shfl_xor_sync(0xffffffffu, de, o);
     const float dlogit = de * e * (1.f - e);
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int col = lane + 32 * q;
-      float dm = 0.f;
-      if (dM) {
-        dm = dM[((size_t)g * d.n + i) * U + col] * inv_sqrt * e + dlogit * wav[q];
-        awa[q] = fmaf(dlogit, mreg[q], awa[q]);
+    for (int v = 0; v < NV; ++v) {
+      const int col = (32 * v + lane) * VW;
+      float dm[VW], dzx[VW];
+#pragma unroll
+      for (int k = 0; k < VW; ++k) {
+        dm[k] = 0.f;
+        if (dM) {
+          dm[k] = fmaf(dmr[v][k], e, dlogit * wav[v][k]);
+          awa[v][k] = fmaf(dlogit, ze[v][k], awa[v][k]);
+        }
+        const float z = zx[v][k], sg = sigm(z);
+        awp[v][k] = fmaf(dp, z * sg, awp[v][k]);
+        dzx[k] = dp * wpv[v][k] * (sg * (1.f + z * (1.f - sg)));
       }
-      DM[row * U + col] = dm;
-      const float zx = Zx[row * U + col];
-      awp[q] = fmaf(dp, silu_f(zx), awp[q]);
-      Zx[row * U + col] = dp * wpv[q] * dsilu_f(zx);
+      stv<VW>(DM + row * U + col, dm);
+      stv<VW>(Zx + row * U + col, dzx);
     }
     aba += dlogit;
     abp += dp;
     if (lane < d.dim) {
       float gv = dc[lane] * pv * inv;
-      if (!isz) gv -= pv * dcv * inv * inv * v[lane] / len;
+      if (!isz) gv -= pv * dcv * inv * inv * v3[lane] / len;
       dvgeo[row * 4 + lane] = gv;
     }
   }
   // block reduction of the vector accumulators
   __shared__ float red[8][2 * 256 + 2];
 #pragma unroll
-  for (int q = 0; q < Q; ++q) { red[warp][lane + 32 * q] = awa[q]; red[warp][U + lane + 32 * q] = awp[q]; }
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      red[warp][(32 * v + lane) * VW + k] = awa[v][k];
+      red[warp][U + (32 * v + lane) * VW + k] = awp[v][k];
+    }
   if (lane == 0) { red[warp][2 * U] = aba; red[warp][2 * U + 1] = abp; }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 2 * U + 2; idx += blockDim.x) {

@@ -237,26 +237,41 @@ cudaError_t launch(const Args& g, int num_sms, cudaStream_t st) {
 constexpr uint32_t IDESC_A_MN = 1u << 15;
 constexpr int DW_NT = 512;
 
-// convert rows [r0, r0 + 32) of a row-major [M x C] matrix into the (hi, lo) images at dst (C * 64 B each); csum (optional)
-// accumulates this thread's share of the column sums (the bias gradient) on the way
-template <int C, bool SUM>
-__device__ __forceinline__ void convert_chunk(const float* __restrict__ src, int M, int r0, int op, unsigned char* dst_hi,
-                                              unsigned char* dst_lo, int tid, float (&csum)[4 * (C / 32) / (512 / 32)][8]) {
-  constexpr int XB = C / 32;                  // blocks of 4 column groups (32 columns) per row
-  constexpr int NW = DW_NT / 32;
-  constexpr int NJ = 4 * XB / NW;             // (row group, block) combinations per warp
+// Rows [r0, r0 + 32) of a row-major [M x C] matrix -> the (hi, lo) images at dst (C * 64 B each), in two steps so that
+// the loads of the next chunk are in flight while this one is converted: load_chunk (coalesced 2 x 16 B per thread and
+// (row group, column block) combination) and convert_chunk (op, bf16 split, conflict-free 16-byte stores); csum
+// (optional) accumulates this thread's share of the column sums (the bias gradient) on the way
+template <int C>
+__device__ __forceinline__ void load_chunk(const float* __restrict__ src, int M, int r0, int tid,
+                                           float4 (&v)[4 * (C / 32) / (512 / 32)][2]) {
+  constexpr int XB = C / 32, NW = 512 / 32, NJ = 4 * XB / NW;
   static_assert(NJ >= 1, "warps");
   const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int combo = warp + NW * j, mg = combo & 3, x = combo >> 2;
     const int m = 8 * mg + (lane & 7), cg = 4 * x + (lane >> 3);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    v[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v[j][1] = v[j][0];
     if (r0 + m < M) {
       const float* p = src + (size_t)(r0 + m) * C + 8 * cg;
-      a = *reinterpret_cast<const float4*>(p);
-      b = *reinterpret_cast<const float4*>(p + 4);
+      v[j][0] = *reinterpret_cast<const float4*>(p);
+      v[j][1] = *reinterpret_cast<const float4*>(p + 4);
     }
+  }
+}
+template <int C, bool SUM>
+__device__ __forceinline__ void convert_chunk(const float4 (&v)[4 * (C / 32) / (512 / 32)][2], int op, unsigned char* dst_hi,
+                                              unsigned char* dst_lo, int tid, float (&csum)[4 * (C / 32) / (512 / 32)][8]) {
+  constexpr int XB = C / 32;                  // blocks of 4 column groups (32 columns) per row
+  constexpr int NW = DW_NT / 32;
+  constexpr int NJ = 4 * XB / NW;             // (row group, block) combinations per warp
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int combo = warp + NW * j, mg = combo & 3, x = combo >> 2;
+    const int m = 8 * mg + (lane & 7), cg = 4 * x + (lane >> 3);
+    float4 a = v[j][0], b = v[j][1];
     if (op) {
       a.x = silu(a.x); a.y = silu(a.y); a.z = silu(a.z); a.w = silu(a.w);
       b.x = silu(b.x); b.y = silu(b.y); b.z = silu(b.z); b.w = silu(b.w);
@@ -299,13 +314,24 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
   for (int j = 0; j < NJB; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) bsum[j][i] = 0.f;
+  float4 na[NJA][2], nb[NJB][2];         // the next chunk, loaded one iteration ahead
+  if (nchunks > 0) { load_chunk<K>(A, m_end, m_begin, tid, na); load_chunk<N>(dZ, m_end, m_begin, tid, nb); }
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
+    float4 ca[NJA][2], cb[NJB][2];
+#pragma unroll
+    for (int j = 0; j < NJA; ++j) { ca[j][0] = na[j][0]; ca[j][1] = na[j][1]; }
+#pragma unroll
+    for (int j = 0; j < NJB; ++j) { cb[j][0] = nb[j][0]; cb[j][1] = nb[j][1]; }
+    if (c + 1 < nchunks) {
+      load_chunk<K>(A, m_end, m_begin + 32 * (c + 1), tid, na);
+      load_chunk<N>(dZ, m_end, m_begin + 32 * (c + 1), tid, nb);
+    }
     if (c >= 2) { mbar_wait(&bar[s], ((c >> 1) - 1) & 1); tc_fence_after(); }     // the MMAs of chunk c-2 have left stage s
     unsigned char* st = smem + s * STAGE;
-    convert_chunk<K, false>(A, m_end, m_begin + 32 * c, a_op, st, st + A_IMG, tid, asum);
-    if (colsum) convert_chunk<N, true>(dZ, m_end, m_begin + 32 * c, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
-    else convert_chunk<N, false>(dZ, m_end, m_begin + 32 * c, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
+    convert_chunk<K, false>(ca, a_op, st, st + A_IMG, tid, asum);
+    if (colsum) convert_chunk<N, true>(cb, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
+    else convert_chunk<N, false>(cb, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
