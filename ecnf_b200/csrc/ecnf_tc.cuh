@@ -87,6 +87,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
+// asynchronous prefetch of a contiguous global range into L2 (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))

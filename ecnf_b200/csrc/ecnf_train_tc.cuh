@@ -34,7 +34,12 @@ struct Args {
 
 // ex2 / rcp based sigmoid (~1e-6 relative, well inside the 3-pass GEMM error): these elementwise ops run on 45 M elements
 // per layer and would otherwise dominate the kernels
-__device__ __forceinline__ float sigm(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ float sigm(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));      // e = inf -> 0, e = 0 -> 1
+  return r;
+}
 __device__ __forceinline__ float silu(float z) { return z * sigm(z); }
 __device__ __forceinline__ float dsilu(float z) {
   const float s = sigm(z);
@@ -205,21 +210,279 @@ __global__ void __launch_bounds__(GEMM_NT, 1) gemm_rows_tc_kernel(const __grid_c
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================================
+// Transposed, warp-specialised version of the same GEMM (the one the edge-row layers use):
+//
+//     C^T[n (TMEM lane), m (column)] = W^T[n][k] (A operand, TENSOR MEMORY) x op(A)^T[k][m] (B operand, shared memory)
+//
+//   * the 128 output features of this CTA's column half are the TMEM lanes, so a warp of epilogue threads reads /
+//     writes 32 consecutive floats of one row of C, z, add ... : every global access of the epilogue is a coalesced
+//     128-byte line and the bias is a per-thread constant -- no shared-memory staging of C;
+//   * the B operand is "MN-major" (8 rows of one k = one 16-byte vector, as in engine A): a producer thread loads the
+//     same k of 8 consecutive rows (a warp load = 128 contiguous bytes of a row), applies op, splits to bf16 (hi, lo)
+//     and stores 16 bytes; a warp stores 512 contiguous bytes -- no shared-memory staging of A either;
+//   * W^T (hi | lo) is written to tensor memory once per CTA; the MMA reads only B from shared memory;
+//   * warps 0-7: epilogue, warps 8-23: producers (global -> registers one chunk ahead -> ring of 64-k chunks),
+//     warp 24: MMA issue; hand-over by mbarriers only (full / empty per ring slot, full / empty per accumulator), so the
+//     loads, the conversion, the MMAs and the epilogue of consecutive tiles overlap freely.
+// =====================================================================================================================
+constexpr int T_NT = 800;       // warps 0-7: epilogue, 8-23: producers, 24: MMA issue
+constexpr int T_KC = 64;                        // k per ring slot
+constexpr int T_IMG = 128 * T_KC * 2;           // one (hi or lo) image of a chunk: [16 row groups][64 k][8 rows] bf16
+constexpr int T_SLOT = 2 * T_IMG;
+constexpr int T_NS = 6;                         // ring slots (192 KB)
+constexpr uint32_t T_LBO = 128, T_SBO = T_KC * 16;
+constexpr uint32_t T_WCOL = 256;                // W^T operand: TMEM columns [256, 256 + K); accumulators [0, 128), [128, 256)
+
+// 32 consecutive rows of one output column: C = ((acc + bias) + resid + add) * silu'(z); the pointers advance by one row
+// (N floats) per step, i.e. by compile-time immediates.  RS / AD / MZ say which operands exist (checked once, uniformly,
+// by the caller), so the loads of a batch are unconditional and issued back to back before the first use.
+template <int N, bool RS, bool AD, bool MZ, bool FULL>
+__device__ __forceinline__ void epi_rows(const Args& g, const uint32_t (&x)[32], size_t o0, float bias, int nrows) {
+  const float* rsp = g.resid + o0;
+  const float* adp = g.add + o0;
+  const float* mzp = g.mulz + o0;
+  float* cp = g.C + o0;
+  constexpr int BT = (RS || AD) ? 8 : 16;      // loads in flight per operand
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += BT) {
+    float ad[BT], rs[BT], mz[BT];
+#pragma unroll
+    for (int j = 0; j < BT; ++j) {
+      const bool ok = FULL || j0 + j < nrows;
+      if (RS) rs[j] = ok ? rsp[(j0 + j) * N] : 0.f;
+      if (AD) ad[j] = ok ? adp[(j0 + j) * N] : 0.f;
+      if (MZ) mz[j] = ok ? mzp[(j0 + j) * N] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < BT; ++j) {
+      float v = __uint_as_float(x[j0 + j]) + bias;
+      if (RS) v += rs[j];
+      if (AD) v += ad[j];
+      if (MZ) v *= dsilu(mz[j]);
+      if (FULL || j0 + j < nrows) cp[(j0 + j) * N] = v;
+    }
+  }
+}
+template <int N, bool RS, bool AD, bool MZ>
+__device__ __forceinline__ void epi_rows_any(const Args& g, const uint32_t (&x)[32], size_t o0, float bias, int nrows) {
+  if (nrows >= 32) epi_rows<N, RS, AD, MZ, true>(g, x, o0, bias, 32);
+  else epi_rows<N, RS, AD, MZ, false>(g, x, o0, bias, nrows);
+}
+
+template <int K, int N>
+__global__ void __launch_bounds__(T_NT, 1) gemm_rows_tcT_kernel(const __grid_constant__ Args g) {
+  static_assert((K == 128 || K == 256) && (N == 128 || N == 256), "shapes");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar_full[T_NS], bar_empty[T_NS], bar_accfull[2], bar_accempty[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) {
+    for (int i = 0; i < T_NS; ++i) { mbar_init(&bar_full[i], 512); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_accfull[i], 1); mbar_init(&bar_accempty[i], 256); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  constexpr int NH = N / 128, NCH = K / T_KC;
+  const int nh = blockIdx.x % NH, tile0 = blockIdx.x / NH, tile_step = gridDim.x / NH;
+  const int ntiles = (g.M + 127) / 128;
+
+  if (warp < 8) {
+    // ================================ epilogue warps ================================
+    const int n = 32 * (warp & 3) + lane, hh = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const int col = 128 * nh + n;
+    {
+      // W[:, col] -> bf16 (hi, lo) pairs of consecutive k -> TMEM; this thread covers k in [hh K/2, (hh+1) K/2)
+      const float* wsrc = g.W + col;
+#pragma unroll 1
+      for (int q = 0; q < K / 64; ++q) {
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = hh * (K / 2) + 32 * q + 2 * j;
+          split_pack(wsrc[(size_t)k * N], wsrc[(size_t)(k + 1) * N], h[j], l[j]);
+        }
+        const uint32_t c0 = T_WCOL + (uint32_t)(hh * (K / 4) + 16 * q);
+        tmem_st16(tmem + lane_addr + c0, h);
+        tmem_st16(tmem + lane_addr + c0 + K / 2, l);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      named_bar_sync(1, 288);
+    }
+    const float bias = g.bias ? g.bias[col] : 0.f;
+    // rows [16 warp, +16) of the tile's blocks of z / add / resid -> L2, one tile ahead of their use
+    auto prefetch_tile = [&](int tile_) {
+      const int row = tile_ * 128 + 16 * warp;
+      if (lane == 0 && tile_ < ntiles && row < g.M) {
+        const uint32_t bytes = (uint32_t)min(16, g.M - row) * N * 4u;
+        if (g.mulz) prefetch_l2_bulk(g.mulz + (size_t)row * N, bytes);
+        if (g.add) prefetch_l2_bulk(g.add + (size_t)row * N, bytes);
+        if (g.resid) prefetch_l2_bulk(g.resid + (size_t)row * N, bytes);
+      }
+    };
+    prefetch_tile(tile0);
+    int t = 0;
+    for (int tile = tile0; tile < ntiles; tile += tile_step, ++t) {
+      const int a = t & 1;
+      prefetch_tile(tile + tile_step);
+      mbar_wait_parked(&bar_accfull[a], (uint32_t)(t >> 1) & 1u, 2000u);
+      tc_fence_after();
+      const int r0 = tile * 128 + 64 * hh;
+#pragma unroll 1
+      for (int b = 0; b < 2; ++b) {
+        uint32_t x[32];
+        tmem_ld32(tmem + 128u * a + lane_addr + (uint32_t)(64 * hh + 32 * b), x);
+        tmem_wait_ld();
+        if (b == 1) {      // the accumulator is in registers: the MMAs of tile t + 2 may overwrite it
+          tc_fence_before();
+          mbar_arrive(&bar_accempty[a]);
+        }
+        const int rb = r0 + 32 * b;
+        const size_t o0 = (size_t)rb * N + col;
+        const int nrows = g.M - rb;
+        const int ops = (g.resid ? 4 : 0) | (g.add ? 2 : 0) | (g.mulz ? 1 : 0);
+        switch (ops) {
+          case 0: epi_rows_any<N, false, false, false>(g, x, o0, bias, nrows); break;
+          case 1: epi_rows_any<N, false, false, true>(g, x, o0, bias, nrows); break;
+          case 2: epi_rows_any<N, false, true, false>(g, x, o0, bias, nrows); break;
+          case 3: epi_rows_any<N, false, true, true>(g, x, o0, bias, nrows); break;
+          case 4: epi_rows_any<N, true, false, false>(g, x, o0, bias, nrows); break;
+          case 5: epi_rows_any<N, true, false, true>(g, x, o0, bias, nrows); break;
+          case 6: epi_rows_any<N, true, true, false>(g, x, o0, bias, nrows); break;
+          default: epi_rows_any<N, true, true, true>(g, x, o0, bias, nrows); break;
+        }
+      }
+    }
+  } else if (warp < 24) {
+    // ================================ producer warps ================================
+    // warp pw owns row group pw (8 rows) of every chunk: lane l loads k = l and k = 32 + l of its 8 rows
+    const int pw = warp - 8;
+    float nx[16];
+    auto fetch = [&](int tile_, int c_) {
+      const int rbase = tile_ * 128 + 8 * pw;
+      const float* src = g.A + (size_t)rbase * K + c_ * T_KC + lane;
+      if (rbase + 8 <= g.M && tile_ < ntiles) {      // all 8 rows exist: immediate offsets, no predicates
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int r = 0; r < 8; ++r) nx[8 * u + r] = src[r * K + 32 * u];
+      } else {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            nx[8 * u + r] = (tile_ < ntiles && rbase + r < g.M) ? src[r * K + 32 * u] : 0.f;
+      }
+    };
+    // my rows of a tile's block of A -> L2, two tiles ahead of the register loads
+    auto prefetch_tile = [&](int tile_) {
+      const int row = tile_ * 128 + 8 * pw;
+      if (lane == 0 && tile_ < ntiles && row < g.M)
+        prefetch_l2_bulk(g.A + (size_t)row * K, (uint32_t)min(8, g.M - row) * K * 4u);
+    };
+    prefetch_tile(tile0 + tile_step);
+    fetch(tile0, 0);
+    int gch = 0;
+    for (int tile = tile0; tile < ntiles; tile += tile_step) {
+      prefetch_tile(tile + 2 * tile_step);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++gch) {
+        float cur[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cur[i] = nx[i];
+        if (c + 1 < NCH) fetch(tile, c + 1);
+        else fetch(tile + tile_step, 0);
+        if (g.a_op) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] = silu(cur[i]);
+        }
+        uint32_t h[2][4], l[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) split_pack(cur[8 * u + 2 * p], cur[8 * u + 2 * p + 1], h[u][p], l[u][p]);
+        const int slot = gch % T_NS, use = gch / T_NS;
+        if (use > 0) mbar_wait_parked(&bar_empty[slot], (uint32_t)(use - 1) & 1u, 1000u);
+        unsigned char* d = smem + slot * T_SLOT + pw * (int)T_SBO + lane * 16;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          *reinterpret_cast<uint4*>(d + u * 512) = make_uint4(h[u][0], h[u][1], h[u][2], h[u][3]);
+          *reinterpret_cast<uint4*>(d + u * 512 + T_IMG) = make_uint4(l[u][0], l[u][1], l[u][2], l[u][3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&bar_full[slot]);
+      }
+    }
+  } else {
+    // ================================ MMA issue warp ================================
+    named_bar_sync(1, 288);      // W^T is in tensor memory
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 128) | IDESC_B_MN;
+      const uint32_t sbase = smem_u32(smem);
+      int gch = 0, t = 0;
+      for (int tile = tile0; tile < ntiles; tile += tile_step, ++t) {
+        const int a = t & 1;
+        if (t >= 2) { while (!mbar_try_wait(&bar_accempty[a], (uint32_t)((t >> 1) - 1) & 1u)) __nanosleep(64); tc_fence_after(); }
+        const uint32_t acc = tmem + 128u * a;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++gch) {
+          const int slot = gch % T_NS, use = gch / T_NS;
+          while (!mbar_try_wait(&bar_full[slot], (uint32_t)use & 1u)) __nanosleep(32);
+          tc_fence_after();
+          const uint32_t bsm = sbase + (uint32_t)slot * T_SLOT;
+#pragma unroll
+          for (int ks = 0; ks < T_KC / 16; ++ks) {
+            const uint64_t bh = make_sdesc(bsm + ks * 2 * T_LBO, T_LBO, T_SBO);
+            const uint64_t bl = make_sdesc(bsm + T_IMG + ks * 2 * T_LBO, T_LBO, T_SBO);
+            const uint32_t a_hi = tmem + T_WCOL + (uint32_t)(c * (T_KC / 2) + ks * 8), a_lo = a_hi + K / 2;
+            mma_ts(acc, a_hi, bh, idesc, (c | ks) ? 1u : 0u);
+            mma_ts(acc, a_lo, bh, idesc, 1u);
+            mma_ts(acc, a_hi, bl, idesc, 1u);
+          }
+          mma_commit(&bar_empty[slot]);
+        }
+        mma_commit(&bar_accfull[a]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 template <int K, int N>
 cudaError_t launch(const Args& g, int num_sms, cudaStream_t st) {
-  const size_t smem = (size_t)2 * 128 * K * sizeof(__nv_bfloat16) + (size_t)128 * STAGE_LD * sizeof(float);
-  auto kern = gemm_rows_tc_kernel<K, N>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   const int ntiles = (g.M + 127) / 128;
   constexpr int NH = N / 128;
   int groups = num_sms / NH;
   if (groups > ntiles) groups = ntiles;
-  kern<<<groups * NH, GEMM_NT, smem, st>>>(g);
+  if (g.rowvec) {          // per-graph row vectors: only the staged kernel adds them
+    const size_t smem = (size_t)2 * 128 * K * sizeof(__nv_bfloat16) + (size_t)128 * STAGE_LD * sizeof(float);
+    auto kern = gemm_rows_tc_kernel<K, N>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    kern<<<groups * NH, GEMM_NT, smem, st>>>(g);
+    return cudaGetLastError();
+  }
+  const size_t smem = (size_t)T_NS * T_SLOT;
+  auto kern = gemm_rows_tcT_kernel<K, N>;
+  static bool configuredT = false;
+  if (!configuredT) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configuredT = true;
+  }
+  kern<<<groups * NH, T_NT, smem, st>>>(g);
   return cudaGetLastError();
 }
 
