@@ -388,22 +388,56 @@ __global__ void edge_gather_kernel(Dims d, const float* __restrict__ xs, const f
       make_float4(a.x + b.x + s * w.x, a.y + b.y + s * w.y, a.z + b.z + s * w.z, a.w + b.w + s * w.w);
 }
 
+// Lane l owns the VW = min(4, U/32) consecutive columns (32 v + l) VW .. of every group v < NV of 32 VW columns, so
+// every access is one 8- or 16-byte vector and a warp covers 32 VW contiguous floats; all loads of a row are issued before
+// the first use, and the elementwise SiLU uses ex2 / rcp (as in ecnf_train_tc.cuh).
+template <int VW> struct VecT;
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+template <int VW>
+__device__ __forceinline__ void ldv(const float* p, float (&o)[VW]) {
+  const typename VecT<VW>::T v = *reinterpret_cast<const typename VecT<VW>::T*>(p);
+  const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+  for (int i = 0; i < VW; ++i) o[i] = f[i];
+}
+template <int VW>
+__device__ __forceinline__ void stv(float* p, const float (&o)[VW]) {
+  typename VecT<VW>::T v;
+  float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+  for (int i = 0; i < VW; ++i) f[i] = o[i];
+  *reinterpret_cast<typename VecT<VW>::T*>(p) = v;
+}
+
 // per edge row (one warp): attention gate e = sigmoid(m.wa + ba), head p = y.wp + bp   (egnn.py:83-85, 99-101)
 template <int U>
 __global__ void edge_heads_kernel(Dims d, const float* __restrict__ Ze, const float* __restrict__ Zx,
                                   const float* __restrict__ wa, const float* __restrict__ ba,
                                   const float* __restrict__ wp, const float* __restrict__ bp, float* __restrict__ eatt,
                                   float* __restrict__ pout) {
+  constexpr int Q = U / 32, VW = Q < 4 ? Q : 4, NV = Q / VW;
+  using ecnf_train_tc::sigm;
   const int lane = threadIdx.x & 31;
   const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (size_t)d.B * d.E) return;
   float sa = 0.f, sp = 0.f;
+  float ze[NV][VW], zx[NV][VW], wav[NV][VW], wpv[NV][VW];
 #pragma unroll
-  for (int q = 0; q < U / 32; ++q) {
-    const int col = lane + 32 * q;
-    sa = fmaf(silu_f(Ze[row * U + col]), wa[col], sa);
-    sp = fmaf(silu_f(Zx[row * U + col]), wp[col], sp);
+  for (int v = 0; v < NV; ++v) {
+    const int col = (32 * v + lane) * VW;
+    ldv<VW>(Ze + row * U + col, ze[v]);
+    ldv<VW>(Zx + row * U + col, zx[v]);
+    ldv<VW>(wa + col, wav[v]);
+    ldv<VW>(wp + col, wpv[v]);
   }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      sa = fmaf(ze[v][k] * sigm(ze[v][k]), wav[v][k], sa);
+      sp = fmaf(zx[v][k] * sigm(zx[v][k]), wpv[v][k], sp);
+    }
   for (int o = 16; o > 0; o >>= 1) {
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
     sp += __shfl_xor_sync(0xffffffffu, sp, o);
@@ -477,28 +511,6 @@ __global__ void loss_kernel(Dims d, const float* __restrict__ xsL, const float* 
 // In:  dM [B*n, U] (grad wrt aggregated message, null in the last block), dxs_next [B, D]
 // Out: DM [EB, U] = grad wrt m from the message path (0 if last); Zx <- d z_x[L-1] (in place);
 //      dvgeo [EB, 4] = grad wrt v_ij from the coordinate path; accumulates d wa, d ba, d wp, d bp.
-// Lane l owns the VW = min(4, U/32) consecutive columns (32 v + l) VW .. of every group v < NV of 32 VW columns, so
-// every access is one 8- or 16-byte vector and a warp covers 32 VW contiguous floats; all loads of a row are issued before
-// the first use, and the elementwise SiLU uses ex2 / rcp (as in ecnf_train_tc.cuh).
-template <int VW> struct VecT;
-template <> struct VecT<2> { using T = float2; };
-template <> struct VecT<4> { using T = float4; };
-template <int VW>
-__device__ __forceinline__ void ldv(const float* p, float (&o)[VW]) {
-  const typename VecT<VW>::T v = *reinterpret_cast<const typename VecT<VW>::T*>(p);
-  const float* f = reinterpret_cast<const float*>(&v);
-#pragma unroll
-  for (int i = 0; i < VW; ++i) o[i] = f[i];
-}
-template <int VW>
-__device__ __forceinline__ void stv(float* p, const float (&o)[VW]) {
-  typename VecT<VW>::T v;
-  float* f = reinterpret_cast<float*>(&v);
-#pragma unroll
-  for (int i = 0; i < VW; ++i) f[i] = o[i];
-  *reinterpret_cast<typename VecT<VW>::T*>(p) = v;
-}
-
 template <int U>
 __global__ void __launch_bounds__(256) heads_bwd_kernel(Dims d, const float* __restrict__ xs, const float* __restrict__ Ze,
                                  float* __restrict__ Zx, const float* __restrict__ eatt, const float* __restrict__ p,

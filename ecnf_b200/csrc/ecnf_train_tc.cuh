@@ -499,11 +499,19 @@ cudaError_t launch(const Args& g, int num_sms, cudaStream_t st) {
 // =====================================================================================================================
 constexpr uint32_t IDESC_A_MN = 1u << 15;
 constexpr int DW_NT = 512;
+constexpr int DW_PF = 3;        // L2 prefetch distance in 32-row chunks
+constexpr int DW_NS = 3;        // ring stages (64 KB each for K = N = 256)
 
 // Rows [r0, r0 + 32) of a row-major [M x C] matrix -> the (hi, lo) images at dst (C * 64 B each), in two steps so that
 // the loads of the next chunk are in flight while this one is converted: load_chunk (coalesced 2 x 16 B per thread and
 // (row group, column block) combination) and convert_chunk (op, bf16 split, conflict-free 16-byte stores); csum
 // (optional) accumulates this thread's share of the column sums (the bias gradient) on the way
+// 256-bit global load (sm_100): 8 consecutive floats, 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 template <int C>
 __device__ __forceinline__ void load_chunk(const float* __restrict__ src, int M, int r0, int tid,
                                            float4 (&v)[4 * (C / 32) / (512 / 32)][2]) {
@@ -518,8 +526,7 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ src, int M,
     v[j][1] = v[j][0];
     if (r0 + m < M) {
       const float* p = src + (size_t)(r0 + m) * C + 8 * cg;
-      v[j][0] = *reinterpret_cast<const float4*>(p);
-      v[j][1] = *reinterpret_cast<const float4*>(p + 4);
+      ldg256(p, v[j][0], v[j][1]);      // one request per 32-byte sector: a warp load = 8 rows x one full 128-byte line
     }
   }
 }
@@ -553,18 +560,21 @@ __device__ __forceinline__ void convert_chunk(const float4 (&v)[4 * (C / 32) / (
 }
 
 template <int K, int N>
-__global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict__ A, int a_op, const float* __restrict__ dZ,
-                                                       float* __restrict__ dW, float* __restrict__ colsum, int M,
-                                                       int rows_per_cta) {
+__global__ void __launch_bounds__(DW_NT + 32, 1) dw_tc_kernel(const float* __restrict__ A, int a_op, const float* __restrict__ dZ,
+                                                            float* __restrict__ dW, float* __restrict__ colsum, int M,
+                                                            int rows_per_cta) {
   static_assert((K == 128 || K == 256) && (N == 128 || N == 256) && (K / 128) * N <= 512, "shapes");
   constexpr int A_IMG = 32 * K * 2, B_IMG = 32 * N * 2;           // bytes of one (hi or lo) image of a 32-row chunk
   constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ __align__(8) uint64_t bar_full[DW_NS], bar_empty[DW_NS], bar_done;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
-  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  if (tid == 32) {
+    for (int i = 0; i < DW_NS; ++i) { mbar_init(&bar_full[i], DW_NT); mbar_init(&bar_empty[i], 1); }
+    mbar_init(&bar_done, 1);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -577,49 +587,71 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
   for (int j = 0; j < NJB; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) bsum[j][i] = 0.f;
-  float4 na[NJA][2], nb[NJB][2];         // the next chunk, loaded one iteration ahead
-  if (nchunks > 0) { load_chunk<K>(A, m_end, m_begin, tid, na); load_chunk<N>(dZ, m_end, m_begin, tid, nb); }
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1;
-    float4 ca[NJA][2], cb[NJB][2];
-#pragma unroll
-    for (int j = 0; j < NJA; ++j) { ca[j][0] = na[j][0]; ca[j][1] = na[j][1]; }
-#pragma unroll
-    for (int j = 0; j < NJB; ++j) { cb[j][0] = nb[j][0]; cb[j][1] = nb[j][1]; }
-    if (c + 1 < nchunks) {
-      load_chunk<K>(A, m_end, m_begin + 32 * (c + 1), tid, na);
-      load_chunk<N>(dZ, m_end, m_begin + 32 * (c + 1), tid, nb);
-    }
-    if (c >= 2) { mbar_wait(&bar[s], ((c >> 1) - 1) & 1); tc_fence_after(); }     // the MMAs of chunk c-2 have left stage s
-    unsigned char* st = smem + s * STAGE;
-    convert_chunk<K, false>(ca, a_op, st, st + A_IMG, tid, asum);
-    if (colsum) convert_chunk<N, true>(cb, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
-    else convert_chunk<N, false>(cb, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
+  if (warp == DW_NT / 32) {
+    // ---- MMA issue warp: chunk c of the ring -> 3 passes x 2 row steps x K/128 lane halves into the accumulators ----
+    if ((tid & 31) == 0) {
       const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_A_MN | IDESC_B_MN;
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
       constexpr uint32_t LBO_A = K * 16, LBO_B = N * 16;
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % DW_NS, use = c / DW_NS;
+        while (!mbar_try_wait(&bar_full[s], (uint32_t)use & 1u)) __nanosleep(32);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * STAGE), a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
 #pragma unroll
-      for (int h = 0; h < K / 128; ++h) {
+        for (int h = 0; h < K / 128; ++h) {
 #pragma unroll
-        for (int ms = 0; ms < 2; ++ms) {
-          const uint64_t ah = make_sdesc(a_hi + h * 2048 + ms * 2 * LBO_A, LBO_A, 128);
-          const uint64_t al = make_sdesc(a_lo + h * 2048 + ms * 2 * LBO_A, LBO_A, 128);
-          const uint64_t bh = make_sdesc(b_hi + ms * 2 * LBO_B, LBO_B, 128);
-          const uint64_t bl = make_sdesc(b_lo + ms * 2 * LBO_B, LBO_B, 128);
-          const uint32_t acc = tmem + (uint32_t)(h * N);
-          mma_ss(acc, ah, bh, idesc, (c > 0 || ms > 0) ? 1u : 0u);
-          mma_ss(acc, al, bh, idesc, 1u);
-          mma_ss(acc, ah, bl, idesc, 1u);
+          for (int ms = 0; ms < 2; ++ms) {
+            const uint64_t ah = make_sdesc(a_hi + h * 2048 + ms * 2 * LBO_A, LBO_A, 128);
+            const uint64_t al = make_sdesc(a_lo + h * 2048 + ms * 2 * LBO_A, LBO_A, 128);
+            const uint64_t bh = make_sdesc(b_hi + ms * 2 * LBO_B, LBO_B, 128);
+            const uint64_t bl = make_sdesc(b_lo + ms * 2 * LBO_B, LBO_B, 128);
+            const uint32_t acc = tmem + (uint32_t)(h * N);
+            mma_ss(acc, ah, bh, idesc, (c > 0 || ms > 0) ? 1u : 0u);
+            mma_ss(acc, al, bh, idesc, 1u);
+            mma_ss(acc, ah, bl, idesc, 1u);
+          }
         }
+        mma_commit(&bar_empty[s]);
       }
-      mma_commit(&bar[s]);
+      mma_commit(&bar_done);
+    }
+  } else {
+    // ---- conversion warps: every warp runs ahead on its own (no CTA barrier), bounded by the ring ----
+    float4 na[NJA][2], nb[NJB][2];         // the next chunk, loaded one iteration ahead
+    if (nchunks > 0) { load_chunk<K>(A, m_end, m_begin, tid, na); load_chunk<N>(dZ, m_end, m_begin, tid, nb); }
+    if (tid < 2 && nchunks > 1) {               // the first DW_PF - 1 chunks after chunk 0 -> L2
+      const int r = m_begin + 32;
+      const uint32_t rows = (uint32_t)min(32 * (DW_PF - 1), m_end - r);
+      if (tid == 0) prefetch_l2_bulk(A + (size_t)r * K, rows * K * 4u);
+      else prefetch_l2_bulk(dZ + (size_t)r * N, rows * N * 4u);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % DW_NS, use = c / DW_NS;
+      float4 ca[NJA][2], cb[NJB][2];
+#pragma unroll
+      for (int j = 0; j < NJA; ++j) { ca[j][0] = na[j][0]; ca[j][1] = na[j][1]; }
+#pragma unroll
+      for (int j = 0; j < NJB; ++j) { cb[j][0] = nb[j][0]; cb[j][1] = nb[j][1]; }
+      if (c + 1 < nchunks) {
+        load_chunk<K>(A, m_end, m_begin + 32 * (c + 1), tid, na);
+        load_chunk<N>(dZ, m_end, m_begin + 32 * (c + 1), tid, nb);
+      }
+      if (tid < 2 && c + DW_PF < nchunks) {      // chunk c + DW_PF of A / dZ (contiguous 32 rows) -> L2
+        const int r = m_begin + 32 * (c + DW_PF);
+        const uint32_t rows = (uint32_t)min(32, m_end - r);
+        if (tid == 0) prefetch_l2_bulk(A + (size_t)r * K, rows * K * 4u);
+        else prefetch_l2_bulk(dZ + (size_t)r * N, rows * N * 4u);
+      }
+      if (use > 0) mbar_wait_parked(&bar_empty[s], (uint32_t)(use - 1) & 1u, 500u);   // the MMAs of chunk c - DW_NS have left stage s
+      unsigned char* st = smem + s * STAGE;
+      convert_chunk<K, false>(ca, a_op, st, st + A_IMG, tid, asum);
+      if (colsum) convert_chunk<N, true>(cb, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
+      else convert_chunk<N, false>(cb, 0, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid, bsum);
+      fence_proxy_async();
+      mbar_arrive(&bar_full[s]);
     }
   }
+  if (warp < DW_NT / 32) {
   if (colsum) {
     // my partial column sums: lanes that differ in the row (lane & 7) hold the same columns
     const int lane = tid & 31;
@@ -636,10 +668,9 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
       }
     }
   }
-  // the last commit covers every MMA issued before it (they all come from thread 0)
+  // bar_done: every MMA has completed
   if (nchunks > 0) {
-    const int c = nchunks - 1;
-    mbar_wait(&bar[c & 1], (c >> 1) & 1);
+    mbar_wait_parked(&bar_done, 0u, 1000u);
     tc_fence_after();
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     const int lane_k = tid & 127, ch = tid >> 7;          // my lane (k within the half) and my quarter of the N columns
@@ -660,6 +691,7 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
       }
     }
   }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -668,7 +700,7 @@ __global__ void __launch_bounds__(DW_NT, 1) dw_tc_kernel(const float* __restrict
 template <int K, int N>
 cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, float* colsum, int M, int num_sms, cudaStream_t st) {
   constexpr int STAGE = 2 * (32 * K * 2) + 2 * (32 * N * 2);
-  const size_t smem = 2 * STAGE;
+  const size_t smem = (size_t)DW_NS * STAGE;
   auto kern = dw_tc_kernel<K, N>;
   static bool configured = false;
   if (!configured) {
@@ -678,7 +710,7 @@ cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, floa
   }
   int rows_per_cta = ((M + num_sms - 1) / num_sms + 31) / 32 * 32;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, DW_NT, smem, st>>>(A, a_op, dZ, dW, colsum, M, rows_per_cta);
+  kern<<<grid, DW_NT + 32, smem, st>>>(A, a_op, dZ, dW, colsum, M, rows_per_cta);
   return cudaGetLastError();
 }
 

@@ -34,6 +34,32 @@ def test_vf_and_div_match_oracle(case, cuda_device):
     assert err < DIV_TOL, (div.cpu().numpy(), div_ref.numpy())
 
 
+# the networks BASELINE.json's configs[2] and configs[3] run (examples/config/qm9.yaml:6-13, aldp.yaml:11-18), at full size
+FULL_SIZE = {
+    "aldp": (22, 3, 3, (64, 64), 32, 22),
+    "qm9pos": (19, 3, 5, (256, 256, 256, 256), 32, 1),
+}
+
+
+@pytest.mark.parametrize("case", list(FULL_SIZE))
+def test_full_size_networks_vf_and_div(case, cuda_device):
+    n, dim, blocks, units, H, nfeat = FULL_SIZE[case]
+    ocfg, flat, tree, ecfg = make_pair(n, dim, blocks, units, H, n_features=nfeat)
+    eng = Engine(ecfg)
+    B = 3
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, n * dim)).astype(np.float32) * 1.3 + 0.2
+    t = rng.uniform(0, 1, B).astype(np.float32)
+    feat = (np.tile(np.arange(n) % nfeat, (B, 1))).astype(np.int32)      # aldp: features = arange(22), targets/data.py:146
+    p64 = O.to_torch(flat, torch.float64)
+    f_ref, div_ref = O.vf_and_exact_div(p64, ocfg, torch.tensor(x, dtype=torch.float64),
+                                        torch.tensor(t, dtype=torch.float64), torch.tensor(feat).long())
+    f, div = eng.apply_div(tree, x, t, feat)
+    assert rel_err(f.cpu().numpy(), f_ref.numpy()) < VF_TOL
+    err = np.abs(div.cpu().numpy() - div_ref.numpy()).max() / (np.abs(div_ref.numpy()).max() + 1.0)
+    assert err < DIV_TOL, (div.cpu().numpy(), div_ref.numpy())
+
+
 def test_coincident_nodes_safe_norm(cuda_device):
     """safe_norm quirk (numerical.py:7-10, SURVEY C#7): |v|^2 fed to phi_e is 1 for coincident nodes."""
     n, dim, blocks, units, H, nfeat = CASES["small_64_32"]
