@@ -386,7 +386,12 @@ __global__ void __launch_bounds__(T_NT, 1) gemm_rows_tcT_kernel(const __grid_con
         prefetch_l2_bulk(g.A + (size_t)row * K, (uint32_t)min(8, g.M - row) * K * 4u);
     };
     prefetch_tile(tile0 + tile_step);
+    // register loads run two chunks ahead of the conversion (nx0: next chunk, nx: the one after)
+    float nx0[16];
     fetch(tile0, 0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) nx0[i] = nx[i];
+    if (NCH > 1) fetch(tile0, 1); else fetch(tile0 + tile_step, 0);
     int gch = 0;
     for (int tile = tile0; tile < ntiles; tile += tile_step) {
       prefetch_tile(tile + 2 * tile_step);
@@ -394,9 +399,9 @@ __global__ void __launch_bounds__(T_NT, 1) gemm_rows_tcT_kernel(const __grid_con
       for (int c = 0; c < NCH; ++c, ++gch) {
         float cur[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) cur[i] = nx[i];
-        if (c + 1 < NCH) fetch(tile, c + 1);
-        else fetch(tile + tile_step, 0);
+        for (int i = 0; i < 16; ++i) { cur[i] = nx0[i]; nx0[i] = nx[i]; }
+        if (c + 2 < NCH) fetch(tile, c + 2);
+        else fetch(tile + tile_step, c + 2 - NCH);
         if (g.a_op) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) cur[i] = silu(cur[i]);
