@@ -72,7 +72,7 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
   ECNF_CHECK_CUDA(cudaMemsetAsync(ws, 0, 256, st));
   if (tc) {
     void* image_ws = reinterpret_cast<char*>(ws) + 256 + (int64_t)grid * a.scratch_stride * (int64_t)sizeof(float);
-    return launch_tc(m, a, grid, image_ws, st);
+    return launch_tc(m, a, grid, image_ws, div, st);
   }
   return div ? launch_uh<true>(m, a, grid, st) : launch_uh<false>(m, a, grid, st);
 }

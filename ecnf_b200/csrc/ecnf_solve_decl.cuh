@@ -27,7 +27,7 @@ struct TcSmemLayout {
 };
 
 // tile tables of the tensor-core engine: which (group, slot) row sits in which accumulator column (ecnf_solve_tc.cuh)
-enum { TT_NODE1 = 0, TT_NODE, TT_FIRST, TT_MID, TT_LAST, TT_COUNT };
+enum { TT_NODE1 = 0, TT_NODE, TT_FIRST, TT_MID, TT_LAST, TT_EDGE1, TT_COUNT };   // *1: primal rows only (no divergence)
 constexpr int TC_TILE_WORDS = 240;   // 128 column + 64 group + 16 header + 16 primal-position + 4 mask words (+ pad)
 struct TcTabs {
   const uint32_t* base;
@@ -63,6 +63,6 @@ bool tc_eligible(const ecnf_model* mdl, bool div);
 int64_t tc_image_bytes(const ecnf_model* mdl);
 int64_t tc_flops_per_eval(const ecnf_model* mdl);
 int tc_tile_table(const ecnf_model* mdl, int kind, uint32_t* out, int64_t cap_words);
-int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cudaStream_t st);
+int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, bool div, cudaStream_t st);
 
 }  // namespace ecnf_solve_detail

@@ -7,10 +7,12 @@ namespace ecnf_solve_detail {
 
 bool tc_eligible(const ecnf_model* mdl, bool div) {
   const ecnf_config& c = mdl->cfg;
-  if (!div || c.mlp_units != TCU || c.n_hidden != TCH || c.n_layers < 2) return false;
+  if (c.mlp_units != TCU || c.n_hidden != TCH || c.n_layers < 2) return false;
   const int D = c.n_frames * c.dim;
   if (1 + D > 127) return false;   // a (node, slot) group must fit one tile: 64 + 1 + 63 columns
-  return make_tc_layout(c.n_frames, c.dim).total_bytes + 1024 <= 227 * 1024;
+  const TcSmemLayout lay = make_tc_layout(c.n_frames, c.dim);
+  if (!div && lay.mrows < c.n_frames) return false;   // primal-only edge tiles aggregate over all receivers at once
+  return lay.total_bytes + 1024 <= 227 * 1024;
 }
 
 namespace {
@@ -90,7 +92,7 @@ int tc_tile_table(const ecnf_model* mdl, int kind, uint32_t* out, int64_t cap_wo
   return cnt;
 }
 
-int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cudaStream_t st) {
+int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, bool div, cudaStream_t st) {
   static TcPrepList list;   // filled per call below (host-side scratch; the call is not re-entrant across threads)
   TcPrepList local{};
   a.img.base = reinterpret_cast<const unsigned char*>(image_ws);
@@ -111,8 +113,13 @@ int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, cu
   const TcSmemLayout L = make_tc_layout(mdl->cfg.n_frames, mdl->cfg.dim);
   a.lay = L;
   const size_t smem = (size_t)L.total_bytes;
-  ECNF_CHECK_CUDA(cudaFuncSetAttribute(ecnf_solve_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ecnf_solve_tc_kernel<<<grid, TC_NT, smem, st>>>(a);
+  if (div) {
+    ECNF_CHECK_CUDA(cudaFuncSetAttribute(ecnf_solve_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ecnf_solve_tc_kernel<true><<<grid, TC_NT, smem, st>>>(a);
+  } else {
+    ECNF_CHECK_CUDA(cudaFuncSetAttribute(ecnf_solve_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ecnf_solve_tc_kernel<false><<<grid, TC_NT, smem, st>>>(a);
+  }
   ECNF_CHECK_CUDA(cudaGetLastError());
   return ECNF_OK;
 }

@@ -49,6 +49,8 @@ __host__ __device__ __forceinline__ int cw_gid(uint32_t w) { return (int)(w & 10
 __host__ __device__ __forceinline__ int cw_q(uint32_t w) { return (int)((w >> 10) & 255u); }
 __host__ __device__ __forceinline__ int cw_pc(uint32_t w) { return (int)((w >> 18) & 63u); }
 enum { TH_NC0 = 0, TH_NC1, TH_N, TH_G0, TH_NG, TH_WIN, TH_FLUSH, TH_IFIRST, TH_ILAST, TH_SEGS };
+// kinds with one row per group (TT_NODE1, TT_EDGE1) pack densely: column = local group index (group words only for the
+// first 64 groups of a tile)
 
 __host__ __device__ inline int tc_macc_rows(int n, int dim) {
   const int ND = 1 + n * dim;
@@ -63,11 +65,11 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
   const int D = n * dim, ND = 1 + D;
   const bool edge = kind >= TT_FIRST;
   const int ngroups = edge ? n * (n - 1) : n;
-  const int r = kind == TT_NODE1 ? 1 : kind == TT_NODE ? ND : kind == TT_FIRST ? 1 + 2 * dim : kind == TT_MID ? ND : 1 + dim;
+  const int r = (kind == TT_NODE1 || kind == TT_EDGE1) ? 1 : kind == TT_NODE ? ND : kind == TT_FIRST ? 1 + 2 * dim : kind == TT_MID ? ND : 1 + dim;
   // message-accumulator window: tiles of the message-passing kinds never span two windows of receivers
   const int window = (kind == TT_FIRST || kind == TT_MID) ? (tc_macc_rows(n, dim) / ND) * (n - 1) : 0;
   // segments start on 8-column chunk boundaries (the activation rule works chunk-wise); all-primal node tiles pack densely
-  const int al = kind == TT_NODE1 ? 1 : 8;
+  const int al = r == 1 ? 1 : 8;
   int tile = 0, used0 = 0, used1 = 0, half = 0, ng = 0, g0 = 0;
   auto tp = [&](int t) { return out + (size_t)t * TC_TILE_WORDS; };
   auto close = [&](int gnext, int flush) {
@@ -117,7 +119,7 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
         const int rem = 64 - used0;
         if (r <= rem) {
           seg(g, used0, 0, r, false);
-          if (out) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)used0 << 8);
+          if (out && ng < 64) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)used0 << 8);
           used0 += r;
           break;
         }
@@ -136,7 +138,7 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
       const int rem = 64 - used1;
       if (r <= rem) {
         seg(g, 64 + used1, 0, r, false);
-        if (out) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)(64 + used1) << 8);
+        if (out && ng < 64) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)(64 + used1) << 8);
         used1 += r;
         break;
       }
@@ -144,7 +146,7 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) 
     }
     ++ng;
   }
-  close(ngroups, window ? 1 : 0);
+  close(ngroups, (window || kind == TT_EDGE1) ? 1 : 0);     // the primal-only edge kind aggregates over one window = all receivers
   return tile;
 }
 
@@ -199,6 +201,8 @@ extern __shared__ __align__(1024) unsigned char smem_tc[];
 #define TCI(field) (reinterpret_cast<int*>(smem_tc + a.lay.field))
 #define TCW(field) (reinterpret_cast<uint32_t*>(smem_tc + a.lay.field))
 
+// DIV = false: sample_cnf without a divergence -- primal rows only (tile kinds TT_NODE1 / TT_EDGE1, no tangent state)
+template <bool DIV>
 struct EngineTC {
   static constexpr int U = TCU, H = TCH;
   static constexpr int NT = TC_NT;
@@ -244,7 +248,7 @@ struct EngineTC {
   __device__ __forceinline__ float* Ph() const { return Mg() + (size_t)n * ND * U; }
 
   __device__ __forceinline__ EngineTC(const KernelArgs& a_)
-      : a(a_), m(a_.m), img(a_.img), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim), ND(1 + a_.m.n * a_.m.dim),
+      : a(a_), m(a_.m), img(a_.img), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim), ND(DIV ? 1 + a_.m.n * a_.m.dim : 1),
         E(a_.m.n * (a_.m.n - 1)), tid(threadIdx.x), f(threadIdx.x & 127), hh((threadIdx.x >> 7) & 1), warp(threadIdx.x >> 5),
         lane(threadIdx.x & 31), is_epi(threadIdx.x < TC_EPI) {
     if (tid == 0) {
@@ -355,6 +359,14 @@ struct EngineTC {
   // follow them.  Segments start on 8-column chunk boundaries, so the primal column of a segment is column 0 of a chunk
   // (a static register) and silu' is a running per-thread scalar; `segs` = which of my 8 chunks start a segment.
   __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int s) {
+    if constexpr (!DIV) {      // every column is a primal row
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float z = v[c] + bias;
+        v[c] = z * __fdividef(1.f, 1.f + __expf(-z));
+      }
+      return;
+    }
     const uint32_t segs = (TCW(hdr)[s * 16 + TH_SEGS] >> (8 * hh)) & 0xffu;
     float cur = 0.f;
 #pragma unroll
@@ -682,12 +694,12 @@ struct EngineTC {
   struct EdgePh {
     EngineTC& e;
     int b, ntiles, NL, kind;   // kind = tile table (TT_FIRST / TT_MID / TT_LAST)
-    bool htan;
+    bool htan, want_msg;       // want_msg: the aggregated messages feed phi_h (every block but the last)
     float wdf, waf, wpf;       // my feature's entry of w_d (|v|^2 column of phi_e layer 0), attention and head weights
     static constexpr bool stream = true;
     __device__ __forceinline__ uint32_t a_col(int q, int) const { return TC_WCOL + 128u * (q & 1); }
     __device__ __forceinline__ int K(int) const { return TCU; }
-    __device__ __forceinline__ int ekind() const { return kind == TT_FIRST ? KIND_FIRST : kind == TT_MID ? KIND_MID : KIND_LAST; }
+    __device__ __forceinline__ int ekind() const { return kind == TT_FIRST ? KIND_FIRST : kind == TT_MID ? KIND_MID : KIND_LAST; }   // TT_EDGE1 has no tangent columns: the value is never used
     __device__ __forceinline__ int wimg(int w) const {
       const TcImgBlock& ib = e.img.blk[b];
       const int L = e.m.L;
@@ -701,10 +713,10 @@ struct EngineTC {
       waf = bp.wa[e.f];
       wpf = bp.wp[e.f];
       for (int i = e.tid; i < D; i += TC_EPI) { TCF(xacc)[i] = 0.f; TCF(dacc)[i] = 0.f; }
-      if (kind != TT_LAST) {
+      if (DIV && kind != TT_LAST)
         for (int i = e.tid; i < D * D; i += TC_EPI) TCF(xtacc)[i] = 0.f;
+      if (want_msg)
         for (int i = e.tid; i < 2 * (a.lay.mrows + 1) * TCU; i += TC_EPI) TCF(macc)[i] = 0.f;
-      }
       // per-edge geometry (egnn.py:73-76, numerical.py:7-10)
       for (int ed = e.tid; ed < e.E; ed += TC_EPI) {
         const int i = ed / (n - 1), jj = ed - i * (n - 1);
@@ -750,7 +762,7 @@ struct EngineTC {
             sd = TCI(egiz)[ed] ? 0.f : 2.f * acc;
           }
           if (q == 0 || htan) { oS = (j * ND + slot) * TCU; oR = (i * ND + slot) * TCU; }
-          if (!(w & CW_DUP) && kind != TT_LAST) mr = ((i - win) * ND + slot) * TCU;
+          if (!(w & CW_DUP) && want_msg) mr = ((i - win) * ND + slot) * TCU;
           ijk = i | (j << 5) | (k << 10);
         }
         TCW(colw)[s * 128 + e.tid] = w;
@@ -803,7 +815,7 @@ struct EngineTC {
       if (w < NL - 1) {
         e.write_B(s, v);
         e.qend(P_EPI_ST);
-        if (w == L - 2 && kind != TT_LAST) messages(s, v);
+        if (w == L - 2 && want_msg) messages(s, v);
         e.qend(P_MSG);
       } else {
         e.qend(P_EPI);
@@ -838,7 +850,22 @@ struct EngineTC {
         *reinterpret_cast<float2*>(TCF(wB) + warp * 64 + 2 * lane) = make_float2(bco[0], bco[1]);
       }
       __syncwarp();
-      {
+      if constexpr (!DIV) {
+        // msg = m e per edge column; the columns of one receiver are consecutive, so a running sum is added to the
+        // receiver's accumulator row whenever the row changes (padding columns go to the dump row)
+        float* mac = TCF(macc) + (size_t)hh * (a.lay.mrows + 1) * TCU + e.f;
+        const float* wa_ = TCF(wA) + warp * 64;
+        const int* mr_ = TCI(colmrow) + s * 128 + 64 * hh;
+        int cur = mr_[0];
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const int mr = mr_[c];
+          if (mr != cur) { mac[cur] += acc; acc = 0.f; cur = mr; }
+          acc = fmaf(v[c], wa_[c], acc);
+        }
+        mac[cur] += acc;
+      } else {
         // msg = m e,  msg-dot = m-dot e + m e (1 - e) (m-dot . wa)   accumulated per (receiver, slot) row; columns
         // that do not contribute (repeated primal, padding) go to the dump row
         float* mac = TCF(macc) + (size_t)hh * (a.lay.mrows + 1) * TCU + e.f;
@@ -921,7 +948,7 @@ struct EngineTC {
       e.epi_bar();
       {
         // stage 2: fixed-order sums over the edges of a receiver
-        const int r = ek == KIND_MID ? e.ND : ek == KIND_LAST ? 1 + dim : 1 + 2 * dim;
+        const int r = !DIV ? 1 : ek == KIND_MID ? e.ND : ek == KIND_LAST ? 1 + dim : 1 + 2 * dim;
         const int g0 = e.hdr(s, TH_G0), ng = e.hdr(s, TH_NG), i_first = e.hdr(s, TH_IFIRST), i_last = e.hdr(s, TH_ILAST);
         const int per = r * dim;
         for (int idx = e.tid; idx < (i_last - i_first + 1) * per; idx += TC_EPI) {
@@ -932,9 +959,12 @@ struct EngineTC {
           const bool per_sender = (ek == KIND_FIRST && q > dim);
           float acc = 0.f;
           for (int lg = ga; lg < gb; ++lg) {
-            const uint32_t gw = TCW(grpw)[s * 64 + lg];
-            const int qsplit = (int)(gw & 255u), colA = (int)((gw >> 8) & 255u), colB = (int)((gw >> 16) & 255u);
-            const int col = q < qsplit ? colA + q : colB + 1 + (q - qsplit);
+            int col = lg;       // primal-only tiles pack densely: column = local group index
+            if constexpr (DIV) {
+              const uint32_t gw = TCW(grpw)[s * 64 + lg];
+              const int qsplit = (int)(gw & 255u), colA = (int)((gw >> 8) & 255u), colB = (int)((gw >> 16) & 255u);
+              col = q < qsplit ? colA + q : colB + 1 + (q - qsplit);
+            }
             const float val = cd[col * 3 + cc];
             if (per_sender) {
               const int ed = g0 + lg, jj = ed - i * (n - 1);
@@ -973,6 +1003,7 @@ struct EngineTC {
         TCF(xs0)[i] = v;
       }
       const float invn = 1.f / (float)n;
+      if constexpr (DIV)
       for (int idx = tid; idx < D * D; idx += TC_EPI) {
         const int ra = idx / D, k = idx - ra * D;
         const int ia = ra / dim, ca = ra - ia * dim, ik = k / dim, ck = k - ik * dim;
@@ -990,8 +1021,9 @@ struct EngineTC {
 #pragma unroll 1
     for (int b = 0; b < m.nblocks; ++b) {
       const bool last = (b == m.nblocks - 1);
-      const bool htan = b > 0;
-      const int ekind = last ? TT_LAST : (b == 0 ? TT_FIRST : TT_MID);
+      const bool htan = DIV && b > 0;
+      const int ekind = !DIV ? TT_EDGE1 : last ? TT_LAST : (b == 0 ? TT_FIRST : TT_MID);
+      const int nkind = DIV ? TT_NODE : TT_NODE1;
       pbeg();
       {
         const int kind = htan ? TT_NODE : TT_NODE1;
@@ -1001,20 +1033,20 @@ struct EngineTC {
       if (is_epi) epi_bar();     // P_s / P_r / P_h / h_in of every node are in global memory
       pend(P_NODE_PRE);
       {
-        EdgePh p{*this, b, a.tabs.cnt[ekind], 2 * m.L - 1, ekind, htan, 0.f, 0.f, 0.f};
+        EdgePh p{*this, b, a.tabs.cnt[ekind], 2 * m.L - 1, ekind, htan, !last, 0.f, 0.f, 0.f};
         run_phase(p);
       }
       if (is_epi) epi_bar();     // coordinate accumulators and aggregated messages complete
       pend(P_EDGE);
       if (!last) {
-        NodePost p{*this, b, a.tabs.cnt[TT_NODE], m.L + 1, TT_NODE, htan};
+        NodePost p{*this, b, a.tabs.cnt[nkind], m.L + 1, nkind, htan};
         run_phase(p);
       }
       if (is_epi) {
         epi_bar();
         const float invnb = 1.f / (float)(n - 1);
         for (int i = tid; i < D; i += TC_EPI) TCF(xs)[i] += TCF(xacc)[i] * invnb;
-        if (!last)
+        if (DIV && !last)
           for (int i = tid; i < D * D; i += TC_EPI) TCF(xt)[i] += TCF(xtacc)[i] * invnb;
         epi_bar();
       }
@@ -1023,7 +1055,7 @@ struct EngineTC {
     if (is_epi) {
       const float fs = m.final_scaling[0];
       for (int i = tid; i < D; i += TC_EPI) fout[i] = (TCF(xs)[i] - TCF(xs0)[i] - TCF(mu)[i % dim]) * fs;
-      if (tid == 0) {
+      if (DIV && tid == 0) {
         const float invnb = 1.f / (float)(n - 1);
         float s = 0.f;
         for (int d = 0; d < D; ++d) s += TCF(xt)[d * D + d] + TCF(dacc)[d] * invnb;
@@ -1034,11 +1066,12 @@ struct EngineTC {
   }
 };
 
+template <bool DIV>
 __global__ void __launch_bounds__(TC_NT, 1) ecnf_solve_tc_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ long long s_traj;
   __shared__ float s_ctl[8];
-  EngineTC eng(a);
-  solve_body<EngineTC, true>(a, eng, s_traj, s_ctl);
+  EngineTC<DIV> eng(a);
+  solve_body<EngineTC<DIV>, DIV>(a, eng, s_traj, s_ctl);
   eng.finish(reinterpret_cast<long long*>(reinterpret_cast<char*>(a.counter) + 64));
 }
 

@@ -144,3 +144,27 @@ def test_tensor_core_engine_is_deterministic_and_agrees_with_simt(case, cuda_dev
     assert rel_err(a[0].cpu().numpy(), c[0].cpu().numpy()) < TOL
     la, lc = a[1].cpu().numpy()[:, 0], c[1].cpu().numpy()[:, 0]
     assert np.abs(la - lc).max() < TOL * (np.abs(lc).max() + 1)
+
+
+@pytest.mark.parametrize("case", ["dw4", "lj13"])
+def test_tensor_core_sample_only_agrees_with_simt_and_oracle(case, cuda_device):
+    """sample_cnf without a divergence (sample_and_log_prob.py:11-38; the path of load_checkpoint_measure_sampling_time.py)
+    on the primal-only tensor-core tiles: deterministic, equal to the fp32 SIMT engine within the 3-pass bf16 error, and
+    equal to the oracle on the first trajectories."""
+    B = 300 if case == "dw4" else 200
+    ocfg, flat, tree, eng, x0, feat = _setup(case, B, seed=33)
+    ctrl = L.make_ctrl(use_fixed_step_size=True)
+    try:
+        eng.lib.ecnf_set_engine(0)
+        a = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, ctrl)
+        b = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, ctrl)
+        assert torch.equal(a[0], b[0])
+        eng.lib.ecnf_set_engine(1)
+        c = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, ctrl)
+    finally:
+        eng.lib.ecnf_set_engine(0)
+    assert (a[2].cpu().numpy()[:, 2] == 121).all()
+    assert rel_err(a[0].cpu().numpy(), c[0].cpu().numpy()) < TOL
+    p32 = O.to_torch(flat, torch.float32)
+    x1_ref, _ = O.sample_cnf(p32, ocfg, x0[:4], torch.tensor(feat[:4]).long(), O.SolveControl(fixed=True))
+    assert rel_err(a[0].cpu().numpy()[:4], x1_ref.numpy()) < TOL

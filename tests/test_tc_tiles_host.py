@@ -28,8 +28,8 @@ def table(eng, kind):
 def test_tile_tables(n, dim):
     eng = Engine(CnfConfig(n, dim, 0.01, 1.0, 3, (128, 128, 128), 64, 8, 1))
     D, ND = n * dim, 1 + n * dim
-    rs = {0: 1, 1: ND, 2: 1 + 2 * dim, 3: ND, 4: 1 + dim}
-    for kind in range(5):
+    rs = {0: 1, 1: ND, 2: 1 + 2 * dim, 3: ND, 4: 1 + dim, 5: 1}     # 5 = primal-only edge rows (sample_cnf, no divergence)
+    for kind in range(6):
         tab = table(eng, kind)
         assert len(tab) > 0
         r, ngroups = rs[kind], (n if kind < 2 else n * (n - 1))
@@ -50,7 +50,7 @@ def test_tile_tables(n, dim):
                     g, q, pc = w & 1023, (w >> 10) & 255, (w >> 18) & 63
                     if w & PRIMAL:
                         assert q == 0 and pc == c
-                        if kind != 0:
+                        if kind not in (0, 5):
                             assert c % 8 == 0                      # chunk-aligned segment start
                             segs |= 1 << (8 * half + c // 8)
                         cur_g, cur_pc, last_q = g, c, 0
@@ -62,17 +62,20 @@ def test_tile_tables(n, dim):
                         seen.add((g, q))
                         lg = g - h[G0]
                         assert 0 <= lg < h[NG]
-                        gw = int(grp[lg])
-                        qs, ca, cb = gw & 255, (gw >> 8) & 255, (gw >> 16) & 255
-                        assert (ca + q if q < qs else cb + 1 + q - qs) == 64 * half + c
+                        if kind in (0, 5):
+                            assert lg == 64 * half + c     # dense packing: column = local group index
+                        if lg < 64:
+                            gw = int(grp[lg])
+                            qs, ca, cb = gw & 255, (gw >> 8) & 255, (gw >> 16) & 255
+                            assert (ca + q if q < qs else cb + 1 + q - qs) == 64 * half + c
                     mask = int(t[224 + (64 * half + c) // 32])
                     assert bool(mask >> ((64 * half + c) % 32) & 1) == bool(w & PRIMAL)
-            if kind != 0:
+            if kind not in (0, 5):
                 assert h[SEGS] == segs
             if kind in (2, 3):   # one receiver window per tile
                 rw = max(1, 40 // ND)
                 rw = min(rw, n)
                 assert h[IFIRST] // rw == h[ILAST] // rw == h[WIN] // rw and h[WIN] % rw == 0
         assert len(seen) == ngroups * r
-        if kind in (2, 3):
+        if kind in (2, 3, 5):
             assert tab[-1][192 + FLUSH] == 1
