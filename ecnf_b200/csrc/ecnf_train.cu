@@ -455,11 +455,18 @@ __global__ void node_aggregate_kernel(Dims d, const float* __restrict__ xs, cons
   const int gi = blockIdx.x, g = gi / d.n, i = gi - g * d.n, tid = threadIdx.x;
   const size_t row0 = (size_t)g * d.E + (size_t)i * (d.n - 1);
   if (want_m) {
+    using ecnf_train_tc::sigm;
     const float sc = rsqrtf((float)(d.n - 1));
-    for (int col = tid; col < d.U; col += blockDim.x) {
-      float s = 0.f;
-      for (int jj = 0; jj < d.n - 1; ++jj) s = fmaf(silu_f(Ze[(row0 + jj) * d.U + col]), eatt[row0 + jj], s);
-      Mout[(size_t)gi * d.U + col] = s * sc;
+    for (int c4 = tid; c4 < d.U / 4; c4 += blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
+      for (int jj = 0; jj < d.n - 1; ++jj) {
+        const float4 z = *reinterpret_cast<const float4*>(Ze + (row0 + jj) * d.U + 4 * c4);
+        const float e = eatt[row0 + jj];
+        s.x = fmaf(z.x * sigm(z.x), e, s.x); s.y = fmaf(z.y * sigm(z.y), e, s.y);
+        s.z = fmaf(z.z * sigm(z.z), e, s.z); s.w = fmaf(z.w * sigm(z.w), e, s.w);
+      }
+      *reinterpret_cast<float4*>(Mout + (size_t)gi * d.U + 4 * c4) = make_float4(s.x * sc, s.y * sc, s.z * sc, s.w * sc);
     }
   }
   if (tid < d.dim) {
@@ -617,44 +624,59 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(Dims d, const float* __r
 
 // per edge row: d|v|^2 = dz_e0 . w_d  ->  dvgeo += 2 d|v|^2 v ;  d w_d += |v|^2 dz_e0
 template <int U>
-__global__ void gather_bwd_edge_kernel(Dims d, const float* __restrict__ xs, const float* __restrict__ dZ,
+__global__ void __launch_bounds__(256) gather_bwd_edge_kernel(Dims d, const float* __restrict__ xs, const float* __restrict__ dZ,
                                        const float* __restrict__ wd, float* __restrict__ dvgeo, float* __restrict__ g_wd,
-                                       int rows_per_warp) {
-  constexpr int Q = U / 32;
+                                       float* __restrict__ g_be, int rows_per_warp) {
+  constexpr int Q = U / 32, VW = Q < 4 ? Q : 4, NV = Q / VW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const size_t EB = (size_t)d.B * d.E;
   const size_t r_begin = ((size_t)blockIdx.x * nw + warp) * rows_per_warp;
   const size_t r_end = min(EB, r_begin + rows_per_warp);
-  float awd[Q], wdv[Q];
+  float awd[NV][VW], abe[NV][VW], wdv[NV][VW];      // d w_d, d b_e0 (column sums of dZ), w_d
 #pragma unroll
-  for (int q = 0; q < Q; ++q) { awd[q] = 0.f; wdv[q] = wd[lane + 32 * q]; }
+  for (int v = 0; v < NV; ++v) {
+    ldv<VW>(wd + (32 * v + lane) * VW, wdv[v]);
+#pragma unroll
+    for (int k = 0; k < VW; ++k) { awd[v][k] = 0.f; abe[v][k] = 0.f; }
+  }
+#pragma unroll 2
   for (size_t row = r_begin; row < r_end; ++row) {
+    float z[NV][VW];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ldv<VW>(dZ + row * U + (32 * v + lane) * VW, z[v]);
     const int g = (int)(row / d.E);
     int i, j;
     edge_nodes((int)(row - (size_t)g * d.E), d.n, i, j);
     const float* xg = xs + (size_t)g * d.D;
-    float v[3] = {0.f, 0.f, 0.f}, s = 0.f;
-    for (int c = 0; c < d.dim; ++c) { v[c] = xg[i * d.dim + c] - xg[j * d.dim + c]; s = fmaf(v[c], v[c], s); }
+    float v3[3] = {0.f, 0.f, 0.f}, s = 0.f;
+    for (int c = 0; c < d.dim; ++c) { v3[c] = xg[i * d.dim + c] - xg[j * d.dim + c]; s = fmaf(v3[c], v3[c], s); }
     const bool isz = (s == 0.f);
     const float s1 = isz ? 1.f : s;
     float ds = 0.f;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const float z = dZ[row * U + lane + 32 * q];
-      ds = fmaf(z, wdv[q], ds);
-      awd[q] = fmaf(s1, z, awd[q]);
-    }
-    for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
-    if (lane < d.dim && !isz) dvgeo[row * 4 + lane] += 2.f * ds * v[lane];
-  }
-  __shared__ float red[8][256];
+    for (int v = 0; v < NV; ++v)
 #pragma unroll
-  for (int q = 0; q < Q; ++q) red[warp][lane + 32 * q] = awd[q];
+      for (int k = 0; k < VW; ++k) {
+        ds = fmaf(z[v][k], wdv[v][k], ds);
+        awd[v][k] = fmaf(s1, z[v][k], awd[v][k]);
+        abe[v][k] += z[v][k];
+      }
+    for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    if (lane < d.dim && !isz) dvgeo[row * 4 + lane] += 2.f * ds * v3[lane];
+  }
+  __shared__ float red[8][2 * 256];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int k = 0; k < VW; ++k) {
+      red[warp][(32 * v + lane) * VW + k] = awd[v][k];
+      red[warp][U + (32 * v + lane) * VW + k] = abe[v][k];
+    }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < U; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < 2 * U; idx += blockDim.x) {
     float sacc = 0.f;
     for (int w = 0; w < nw; ++w) sacc += red[w][idx];
-    atomicAdd(g_wd + idx, sacc);
+    atomicAdd((idx < U ? g_wd : g_be - U) + idx, sacc);
   }
 }
 
@@ -665,16 +687,23 @@ __global__ void gather_bwd_node_kernel(Dims d, const float* __restrict__ dZ, con
                                        float* __restrict__ dPr, float* __restrict__ dxs) {
   const int ga = blockIdx.x, g = ga / d.n, a = ga - g * d.n, tid = threadIdx.x;
   const size_t e0 = (size_t)g * d.E;
-  for (int col = tid; col < d.U; col += blockDim.x) {
-    float sr = 0.f, ss = 0.f;
-    for (int jj = 0; jj < d.n - 1; ++jj) sr += dZ[(e0 + (size_t)a * (d.n - 1) + jj) * d.U + col];
-    for (int i = 0; i < d.n; ++i) {
-      if (i == a) continue;
-      int jj = a - i - 1; if (jj < 0) jj += d.n;
-      ss += dZ[(e0 + (size_t)i * (d.n - 1) + jj) * d.U + col];
+  // one float4 column group per thread; the loads of the unrolled edge loops are independent (HBM / L2 bound)
+  for (int c4 = tid; c4 < d.U / 4; c4 += blockDim.x) {
+    float4 sr = make_float4(0.f, 0.f, 0.f, 0.f), ss = sr;
+    const float* base = dZ + e0 * d.U + 4 * c4;
+#pragma unroll 6
+    for (int jj = 0; jj < d.n - 1; ++jj) {
+      const float4 z = *reinterpret_cast<const float4*>(base + ((size_t)a * (d.n - 1) + jj) * d.U);
+      sr.x += z.x; sr.y += z.y; sr.z += z.z; sr.w += z.w;
     }
-    dPr[(size_t)ga * d.U + col] = sr;
-    dPs[(size_t)ga * d.U + col] = ss;
+#pragma unroll 6
+    for (int k = 1; k < d.n; ++k) {            // senders i = a + k (mod n): their edge to a is slot jj = n - 1 - k
+      int i = a + k; if (i >= d.n) i -= d.n;
+      const float4 z = *reinterpret_cast<const float4*>(base + ((size_t)i * (d.n - 1) + (d.n - 1 - k)) * d.U);
+      ss.x += z.x; ss.y += z.y; ss.z += z.z; ss.w += z.w;
+    }
+    *reinterpret_cast<float4*>(dPr + (size_t)ga * d.U + 4 * c4) = sr;
+    *reinterpret_cast<float4*>(dPs + (size_t)ga * d.U + 4 * c4) = ss;
   }
   if (dxs && tid < d.dim) {
     float acc = dxs_next[(size_t)g * d.D + a * d.dim + tid];
@@ -863,7 +892,7 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
     }
     edge_heads_kernel<U><<<(unsigned)((EB + 7) / 8), 256, 0, st>>>(d, Ze[b][L - 1], Zx[b][L - 1], p.wa, p.ba, p.wp, p.bp,
                                                                  eb[b], pb[b]);
-    node_aggregate_kernel<<<(unsigned)NB, 128, 0, st>>>(d, xs[b], Ze[b][L - 1], eb[b], pb[b], Mb[b], xs[b + 1], !last);
+    node_aggregate_kernel<<<(unsigned)NB, U / 4 < 32 ? 32 : U / 4, 0, st>>>(d, xs[b], Ze[b][L - 1], eb[b], pb[b], Mb[b], xs[b + 1], !last);
     if (!last) {
       GemmArgs g = gemm_args(Mb[b], p.Wh[0], Zh[b][0], (int)NB);
       g.A2 = hin[b]; g.W2 = p.Wh[0] + (size_t)U * U; g.bias = p.bh[0];
@@ -942,10 +971,11 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
       if ((rc = launch_gemm<U, U, H>(g, sms, st))) return rc;
     }
     // first phi_e layer: gather backward
-    colsum(Ze[b][0], EB, U, gp.be[0]);
+    // first phi_e layer: d|v|^2 -> dvgeo, d w_d and the bias gradient (column sums of dZ_e0) in one pass over dZ_e0
     gather_bwd_edge_kernel<U><<<heads_grid, 256, 0, st>>>(d, xs[b], Ze[b][0], p.We[0] + (size_t)2 * H * U, dvgeo,
-                                                         const_cast<float*>(gp.We[0]) + (size_t)2 * H * U, rows_per_warp);
-    gather_bwd_node_kernel<<<(unsigned)NB, 128, 0, st>>>(d, Ze[b][0], dvgeo, dxs[cur], Ps, Pr, b > 0 ? dxs[cur ^ 1] : nullptr);
+                                                         const_cast<float*>(gp.We[0]) + (size_t)2 * H * U,
+                                                         const_cast<float*>(gp.be[0]), rows_per_warp);
+    gather_bwd_node_kernel<<<(unsigned)NB, U / 4 < 32 ? 32 : U / 4, 0, st>>>(d, Ze[b][0], dvgeo, dxs[cur], Ps, Pr, b > 0 ? dxs[cur ^ 1] : nullptr);
     if ((rc = launch_dw(hin[b], H, 0, Ps, U, const_cast<float*>(gp.We[0]), H, U, (int)NB, sms, st))) return rc;
     if ((rc = launch_dw(hin[b], H, 0, Pr, U, const_cast<float*>(gp.We[0]) + (size_t)H * U, H, U, (int)NB, sms, st))) return rc;
     {
