@@ -318,6 +318,23 @@ def main():
     extra = {}
     launches = args.steps * 3 + e2e_steps * 4
     if not args.no_train:
+        # ---- secondary: plain sampling without a divergence (sample_cnf; BASELINE.json configs[4], the reference's
+        #      load_checkpoint_measure_sampling_time.py path), LJ13, 4736 trajectories per GPU, device-resident noise
+        Bs = min(B, 148 * 32)
+        eng.solve(params, L.MODE_SAMPLE, x0_res[:Bs], feat[:Bs], ctrl)
+        barrier()
+        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sa.record()
+        eng.solve(params, L.MODE_SAMPLE, x0_res[:Bs], feat[:Bs], ctrl)
+        sb.record()
+        barrier()
+        s_ms = torch.tensor([sa.elapsed_time(sb)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(s_ms, op=dist.ReduceOp.MAX)
+        extra["sample_only"] = {"metric": "LJ13 sample_cnf samples/s (no divergence, Dopri5 " + ("adaptive" if args.adaptive else "dt=0.05") + ")",
+                                "value": world * Bs / (s_ms.item() * 1e-3), "unit": "samples/s", "batch_per_gpu": Bs,
+                                "ms": s_ms.item()}
+        launches += 2 * 3
         extra["fm_train"] = bench_train(args, dev, rank, world)
         launches += extra["fm_train"].pop("_launches")
 

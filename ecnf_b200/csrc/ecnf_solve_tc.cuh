@@ -359,11 +359,20 @@ struct EngineTC {
   // follow them.  Segments start on 8-column chunk boundaries, so the primal column of a segment is column 0 of a chunk
   // (a static register) and silu' is a running per-thread scalar; `segs` = which of my 8 chunks start a segment.
   __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int s) {
-    if constexpr (!DIV) {      // every column is a primal row
+    if constexpr (!DIV) {      // every column is a primal row; chunks beyond the used columns of my half are skipped
+      const int nc = hdr(s, TH_NC0 + hh);   // (the sigmoid is MUFU bound and these tiles are mostly padding)
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float z = v[c] + bias;
-        v[c] = z * __fdividef(1.f, 1.f + __expf(-z));
+      for (int ch = 0; ch < 8; ++ch) {
+        if (8 * ch < nc) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float z = v[8 * ch + u] + bias;
+            v[8 * ch + u] = z * __fdividef(1.f, 1.f + __expf(-z));
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[8 * ch + u] = 0.f;
+        }
       }
       return;
     }
