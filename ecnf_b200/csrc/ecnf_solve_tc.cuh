@@ -291,6 +291,8 @@ struct EngineTC {
 
   // ---- hand-over between the epilogue threads and the MMA-issue warp ----------------------------------------------
   __device__ __forceinline__ void epi_bar() const { named_bar_sync(1, TC_EPI); }
+  // the four warps that own one column half (their partial dot products are summed by each of them)
+  __device__ __forceinline__ void half_bar() const { named_bar_sync(2 + hh, TC_EPI / 2); }
   __device__ __forceinline__ void wait_slot(uint64_t* bar, int s) {
     const uint32_t par = (s ? ph1 : ph0) & 1u;
     mbar_wait_parked(bar, par, 20000u);
@@ -796,14 +798,21 @@ struct EngineTC {
 #pragma unroll
       for (int cb = 0; cb < 64; cb += 16) {
         float pa[16], pb[16];
+        const int c0 = s * 128 + 64 * e.hh + cb;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int col = s * 128 + 64 * e.hh + cb + u;
-          pa[u] = ps[TCI(coloffS)[col]];
-          pb[u] = pr[TCI(coloffR)[col]];
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int4 oS = reinterpret_cast<const int4*>(TCI(coloffS) + c0)[u4], oR = reinterpret_cast<const int4*>(TCI(coloffR) + c0)[u4];
+          pa[4 * u4] = ps[oS.x]; pa[4 * u4 + 1] = ps[oS.y]; pa[4 * u4 + 2] = ps[oS.z]; pa[4 * u4 + 3] = ps[oS.w];
+          pb[4 * u4] = pr[oR.x]; pb[4 * u4 + 1] = pr[oR.y]; pb[4 * u4 + 2] = pr[oR.z]; pb[4 * u4 + 3] = pr[oR.w];
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[cb + u] = fmaf(TCF(colsd)[s * 128 + 64 * e.hh + cb + u], wdf, pa[u] + pb[u]);
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const float4 sd = reinterpret_cast<const float4*>(TCF(colsd) + c0)[u4];
+          v[cb + 4 * u4] = fmaf(sd.x, wdf, pa[4 * u4] + pb[4 * u4]);
+          v[cb + 4 * u4 + 1] = fmaf(sd.y, wdf, pa[4 * u4 + 1] + pb[4 * u4 + 1]);
+          v[cb + 4 * u4 + 2] = fmaf(sd.z, wdf, pa[4 * u4 + 2] + pb[4 * u4 + 2]);
+          v[cb + 4 * u4 + 3] = fmaf(sd.w, wdf, pa[4 * u4 + 3] + pb[4 * u4 + 3]);
+        }
       }
       e.qend(P_GATHER);
       e.act_rule(v, 0.f, s);
@@ -839,7 +848,7 @@ struct EngineTC {
       const int hh = e.hh, lane = e.lane, warp = e.warp;
       float* pd = TCF(pdot) + s * 512;
       e.warp_dot(v, waf, pd + warp * 64);
-      e.epi_bar();
+      e.half_bar();
       {
         const float bav = bp.ba[0];
         const float* p4 = pd + (4 * hh) * 64;
@@ -890,15 +899,18 @@ struct EngineTC {
           eg = st ? wa_[8 * ch] : eg;
           // the 8 columns of a chunk belong to one edge: distinct accumulator rows (padding shares the dump row), so
           // the loads need not wait for the stores
+          const int4 ma = reinterpret_cast<const int4*>(mr_)[2 * ch], mb = reinterpret_cast<const int4*>(mr_)[2 * ch + 1];
+          const float4 wa4 = reinterpret_cast<const float4*>(wb_)[2 * ch], wb4 = reinterpret_cast<const float4*>(wb_)[2 * ch + 1];
+          const int mr[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+          const float wbv[8] = {wa4.x, wa4.y, wa4.z, wa4.w, wb4.x, wb4.y, wb4.z, wb4.w};
           float x[8], old[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int c = 8 * ch + u;
-            x[u] = fmaf(curm, wb_[c], v[c] * eg);
-            old[u] = mac[mr_[c]];
+            x[u] = fmaf(curm, wbv[u], v[8 * ch + u] * eg);
+            old[u] = mac[mr[u]];
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) mac[mr_[8 * ch + u]] = old[u] + x[u];
+          for (int u = 0; u < 8; ++u) mac[mr[u]] = old[u] + x[u];
         }
       }
       if (e.hdr(s, TH_FLUSH)) {
@@ -926,13 +938,13 @@ struct EngineTC {
       const int ek = ekind();
       float* pd = TCF(pdot) + s * 512;
       e.warp_dot(v, wpf, pd + e.warp * 64);
-      e.epi_bar();
+      e.half_bar();
       const float bpv = bp.bp[0];
       float* cd = TCF(cdbuf) + s * 384;
       // stage 1: one (column, coordinate) contribution per thread
       for (int cc = 0; cc < dim; ++cc) {
-        const int col = e.tid & 127;
-        if ((e.tid >> 7) != (cc & 1)) continue;     // halves of the CTA alternate over the coordinates
+        const int col = 64 * e.hh + (e.f & 63);     // a column of my own half (only its partial dots are complete)
+        if ((e.f >> 6) != (cc & 1)) continue;       // the two 64-thread groups of a half alternate over the coordinates
         const uint32_t cw = TCW(colw)[s * 128 + col];
         float val = 0.f;
         if ((cw & CW_VALID) && !(cw & CW_DUP)) {
