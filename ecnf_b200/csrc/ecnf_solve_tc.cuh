@@ -52,6 +52,14 @@ enum { TH_NC0 = 0, TH_NC1, TH_N, TH_G0, TH_NG, TH_WIN, TH_FLUSH, TH_IFIRST, TH_I
 // kinds with one row per group (TT_NODE1, TT_EDGE1) pack densely: column = local group index (group words only for the
 // first 64 groups of a tile)
 
+// sigmoid from ex2.approx / rcp.approx (5 instructions, ~1e-7 absolute: well inside the 3-pass GEMM error)
+__device__ __forceinline__ float fast_sigmoid(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+
 __host__ __device__ inline int tc_macc_rows(int n, int dim) {
   const int ND = 1 + n * dim;
   const int rw = 40 / ND > 1 ? 40 / ND : 1;
@@ -369,7 +377,7 @@ struct EngineTC {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float z = v[8 * ch + u] + bias;
-            v[8 * ch + u] = z * __fdividef(1.f, 1.f + __expf(-z));
+            v[8 * ch + u] = z * fast_sigmoid(z);
           }
         } else {
 #pragma unroll
@@ -384,7 +392,7 @@ struct EngineTC {
     for (int ch = 0; ch < 8; ++ch) {
       if ((segs >> ch) & 1u) {
         const float z = v[8 * ch] + bias;
-        const float sg = __fdividef(1.f, 1.f + __expf(-z));
+        const float sg = fast_sigmoid(z);
         cur = sg * (1.f + z * (1.f - sg));
         v[8 * ch] = z * sg;
       } else {
