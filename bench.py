@@ -38,7 +38,7 @@ QM9 = dict(n_frames=19, dim=3, sigma_min=1e-6, base_scale=2.0, n_blocks_egnn=5, 
            n_invariant_feat_hidden=32, time_embedding_dim=8, n_features=1)
 N_EVALS_FIXED = 121          # 1 FSAL init + 6 stages x 20 steps (dt = 0.05)
 # one ncu --set full capture of ecnf_solve_tc_kernel (profiles/r1_solve_tc_full.txt): dram read + write bytes per trajectory
-NCU_DRAM_BYTES_PER_TRAJ = (20.111925e9 + 43.133786e9) / 148   # ncu --set full, 148 trajectories, 2026-10-18
+NCU_DRAM_BYTES_PER_TRAJ = (19.957129e9 + 43.069807e9) / 148   # ncu --set full, 148 trajectories (profiles/r1_solve_tc_full.txt)
 METRIC = "LJ13 samples/s with exact log-q (Dopri5)"
 UNIT = "samples/s"
 
