@@ -423,14 +423,15 @@ def bench_train(args, dev, rank, world):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item() / K
-    flops = 3.0 * fwd_flops(QM9) * B * world
+    flops = 3.0 * fwd_flops(QM9) * B                     # per GPU (weak scaling: every rank steps its own 512 graphs)
     pk, _ = peaks()
     tf = flops / (ms_step * 1e-3) / 1e12
     return {"metric": "QM9-positional FM train steps/s (batch 512 per GPU, loss+grad+Adam+EMA, H2D of the batch inside)",
             "value": 1e3 / ms_step, "unit": "steps/s", "ms_per_step": ms_step, "loss": loss,
+            "global_batch": B * world, "graphs_per_s": B * world * 1e3 / ms_step,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
                          "unit": "TFLOP/s", "frac": tf / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
-                         "algorithmic_flops_per_step": flops},
+                         "algorithmic_flops_per_step": flops, "per": "GPU"},
             "_launches": 13 * 360}
 
 
