@@ -166,7 +166,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "lj13_sample_and_log_prob_exact_dopri5_fixed_dt0.05", "batch_per_step": n_traj,
+        "config": {"workload": "lj13_sample_and_log_prob_exact_dopri5_fixed_dt0.05+lj_log_weights+ess", "batch_per_step": n_traj,
                    "n_evals_per_sample": N_EVALS_FIXED},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n_traj} LJ13 trajectories per step (121 evals each), torch-CPU fp32 restatement "
