@@ -4,6 +4,7 @@ from typing import Any, NamedTuple, Optional
 import torch
 
 from ..engine import PackedParams, split_key
+from ..utils import jax_random as jr
 from ..utils.optim import Adam, AdamState
 from .core import FlowMatchingCNF
 from .loss import flow_matching_loss_and_grad_fn
@@ -27,7 +28,8 @@ def flow_matching_update_fn(cnf: FlowMatchingCNF, opt_update, state: TrainingSta
     if not isinstance(opt, Adam):
         raise TypeError("opt_update must be ecnf_b200.utils.optim.Adam(...).update")
     eng = cnf.engine
-    key, subkey = split_key(state.key, 2)
+    # gradient_step.py:30: key, subkey = jax.random.split(state.key) -- exact for a jax-style key, SplitMix64 for integer seeds
+    key, subkey = jr.split(state.key) if jr.is_key(state.key) else split_key(state.key, 2)
     packed = eng.pack(state.params)
     loss, grad = flow_matching_loss_and_grad_fn(cnf, packed, x_data, subkey, features, x0=x0, t=t,
                                                 global_offset=global_offset, loss_denominator=loss_denominator)

@@ -4,8 +4,9 @@ accepted directly and every trajectory runs its own adaptive Dopri5 loop on the 
 
 Differences, all documented in DESIGN.md:
   * `approx=True` runs the Hutchinson estimator with one fixed probe per trajectory (`eps=` injects it);
-  * noise can be injected (`x0=`) so parity tests bypass the RNG; without it the base draw comes from the
-    library's Philox stream keyed by (key, global sample index), not from jax threefry;
+  * noise can be injected (`x0=`) so parity tests bypass the RNG; a jax-style key (uint32[2], or [B, 2] per-trajectory
+    keys) reproduces the reference's threefry draws on the host (utils/jax_random.py); an integer seed uses the library's
+    Philox stream keyed by (seed, global sample index) on the device (the fast path);
   * the fixed-step branch of sample_and_log_prob_cnf integrates (x0, 0) -- the reference passes y0=x0 there and
     cannot run (sample_and_log_prob.py:140).
 """
@@ -14,6 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from .. import lib as L
+from ..utils import jax_random as jr
 from .core import FlowMatchingCNF
 
 
@@ -27,6 +29,28 @@ def _batch(features, n_frames: int, n_samples: Optional[int]):
     return 1, True
 
 
+def _jax_keys(key, B: int):
+    """Per-trajectory jax keys: [B, 2] as given, a single key for one trajectory, or `jax.random.split(key, B)` -- what the
+    reference's callers vmap over (setup_training.py:47)."""
+    k = jr.as_key(key)
+    if k.ndim == 1:
+        return k[None] if B == 1 else jr.split(k, B)
+    return k.reshape(-1, 2)
+
+
+def _jax_base_and_eps(eng, key, B: int, want_eps: bool):
+    """x0 = cnf.sample_base(key_i, 1)[0] per trajectory and (Hutchinson) eps_i = jax.random.normal(key_i, (D,)), the raw
+    noise under the same key (sample_and_log_prob.py:55,130; SURVEY C#6), restated on the host."""
+    c = eng.cfg
+    keys = _jax_keys(key, B)
+    x0 = torch.from_numpy(jr.sample_base_per_key(keys, c.n_frames, c.dim, c.base_scale)).to(eng.device)
+    eps = None
+    if want_eps:
+        import numpy as np
+        eps = torch.from_numpy(np.stack([jr.normal(k, (c.D,)) for k in keys])).to(eng.device)
+    return x0, eps
+
+
 def sample_cnf(cnf: FlowMatchingCNF, params, key, features=None, use_fixed_step_size: bool = False,
                rtol: float = 1e-5, atol: float = 1e-5, step_size: float = 0.05, *, n_samples: Optional[int] = None,
                x0=None, global_offset: int = 0, return_stats: bool = False):
@@ -38,7 +62,12 @@ def sample_cnf(cnf: FlowMatchingCNF, params, key, features=None, use_fixed_step_
         x0 = x0.reshape(-1, eng.cfg.D)
     else:
         B, single = _batch(features, eng.cfg.n_frames, n_samples)
-        x0 = eng.base_sample(key, B, global_offset)
+        if jr.is_key(key):
+            if jr.as_key(key).ndim == 2:
+                B, single = jr.as_key(key).shape[0], False
+            x0, _ = _jax_base_and_eps(eng, key, B, False)
+        else:
+            x0 = eng.base_sample(key, B, global_offset)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
     x1, _, stats = eng.solve(params, L.MODE_SAMPLE, x0, features, ctrl)
     out = x1[0] if single else x1
@@ -56,7 +85,11 @@ def get_log_prob(cnf: FlowMatchingCNF, params, x, key=None, features=None, appro
     x = x.reshape(-1, eng.cfg.D)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
     if approx and eps is None:
-        eps = eng.normal_noise(key, x.shape[0], global_offset, substream=1)
+        if jr.is_key(key):
+            import numpy as np
+            eps = torch.from_numpy(np.stack([jr.normal(k, (eng.cfg.D,)) for k in _jax_keys(key, x.shape[0])])).to(eng.device)
+        else:
+            eps = eng.normal_noise(key, x.shape[0], global_offset, substream=1)
     _, logs, stats = eng.solve(params, L.MODE_LOGPROB, x, features, ctrl, eps=eps if approx else None)
     out = (logs[0, 0], logs[0, 1], logs[0, 2]) if single else (logs[:, 0], logs[:, 1], logs[:, 2])
     return (*out, stats) if return_stats else out
@@ -76,7 +109,13 @@ def sample_and_log_prob_cnf(cnf: FlowMatchingCNF, params, key, features=None, ap
         x0 = x0.reshape(-1, eng.cfg.D)
     else:
         B, single = _batch(features, eng.cfg.n_frames, n_samples)
-        x0 = eng.base_sample(key, B, global_offset)
+        if jr.is_key(key):
+            if jr.as_key(key).ndim == 2:
+                B, single = jr.as_key(key).shape[0], False
+            x0, eps_j = _jax_base_and_eps(eng, key, B, approx and eps is None)
+            eps = eps_j if eps is None else eps
+        else:
+            x0 = eng.base_sample(key, B, global_offset)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
     if approx and eps is None:
         eps = eng.normal_noise(key, x0.shape[0], global_offset, substream=0)
