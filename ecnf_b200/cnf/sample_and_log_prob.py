@@ -46,8 +46,7 @@ def _jax_base_and_eps(eng, key, B: int, want_eps: bool):
     x0 = torch.from_numpy(jr.sample_base_per_key(keys, c.n_frames, c.dim, c.base_scale)).to(eng.device)
     eps = None
     if want_eps:
-        import numpy as np
-        eps = torch.from_numpy(np.stack([jr.normal(k, (c.D,)) for k in keys])).to(eng.device)
+        eps = torch.from_numpy(jr.normal_per_key(keys, c.D)).to(eng.device)
     return x0, eps
 
 
@@ -86,8 +85,7 @@ def get_log_prob(cnf: FlowMatchingCNF, params, x, key=None, features=None, appro
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
     if approx and eps is None:
         if jr.is_key(key):
-            import numpy as np
-            eps = torch.from_numpy(np.stack([jr.normal(k, (eng.cfg.D,)) for k in _jax_keys(key, x.shape[0])])).to(eng.device)
+            eps = torch.from_numpy(jr.normal_per_key(_jax_keys(key, x.shape[0]), eng.cfg.D)).to(eng.device)
         else:
             eps = eng.normal_noise(key, x.shape[0], global_offset, substream=1)
     _, logs, stats = eng.solve(params, L.MODE_LOGPROB, x, features, ctrl, eps=eps if approx else None)

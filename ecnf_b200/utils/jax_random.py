@@ -73,8 +73,8 @@ def _rotl(x: np.ndarray, r: int) -> np.ndarray:
 def threefry2x32(key: np.ndarray, x0: np.ndarray, x1: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """The Threefry-2x32 block function, 20 rounds (Salmon et al. 2011; jax._src.prng._threefry2x32_lowering)."""
     with np.errstate(over="ignore"):
-        k0, k1 = _U32(key[0]), _U32(key[1])
-        ks = (k0, k1, _U32(k0 ^ k1 ^ _U32(0x1BD11BDA)))
+        k0, k1 = np.asarray(key[0], _U32), np.asarray(key[1], _U32)      # scalars, or arrays broadcast against x0 / x1
+        ks = (k0, k1, (k0 ^ k1 ^ _U32(0x1BD11BDA)).astype(_U32))
         x0 = x0.astype(_U32) + ks[0]
         x1 = x1.astype(_U32) + ks[1]
         for i in range(5):
@@ -155,10 +155,26 @@ def sample_base(key, n: int, n_nodes: int, dim: int, base_scale: float) -> np.nd
     return (x.reshape(n, n_nodes * dim) * np.float32(base_scale)).astype(np.float32)
 
 
+def normal_per_key(keys, size: int) -> np.ndarray:
+    """vmap over keys of `jax.random.normal(key, (size,))` -> [B, size], all keys in one vectorised threefry pass."""
+    keys = as_key(keys).reshape(-1, 2)
+    count = np.arange(size + (size % 2), dtype=_U32)
+    count[size:] = 0                                       # odd sizes: one ZERO padding counter, last output dropped
+    h = count.size // 2
+    kb = (keys[:, 0:1], keys[:, 1:2])                      # [B, 1] key words broadcast against the counter halves
+    a, b = threefry2x32(kb, count[None, :h], count[None, h:])
+    bits = np.concatenate([a, b], axis=1)[:, :size]
+    lo = np.nextafter(np.float32(-1), np.float32(0))
+    floats = ((bits >> _U32(9)) | _U32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    u = np.maximum(lo, (floats * (np.float32(1.0) - lo) + lo).astype(np.float32))
+    return (np.float32(np.sqrt(2)) * erf_inv(u)).astype(np.float32)
+
+
 def sample_base_per_key(keys, n_nodes: int, dim: int, base_scale: float) -> np.ndarray:
     """vmap over keys of `cnf.sample_base(key, 1)[0]` (sample_and_log_prob.py:24 under setup_training.py:47) -> [B, D]."""
-    keys = as_key(keys).reshape(-1, 2)
-    return np.concatenate([sample_base(k, 1, n_nodes, dim, base_scale) for k in keys], axis=0)
+    x = normal_per_key(keys, n_nodes * dim).reshape(-1, n_nodes, dim)
+    x = x - x.mean(axis=-2, keepdims=True, dtype=np.float32)
+    return (x.reshape(-1, n_nodes * dim) * np.float32(base_scale)).astype(np.float32)
 
 
 def fm_noise(key, batch: int, n_nodes: int, dim: int, base_scale: float) -> Tuple[np.ndarray, np.ndarray]:

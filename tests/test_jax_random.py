@@ -55,4 +55,7 @@ def test_reference_draws_compose_as_in_loss_py():
     keys = jr.split(key, B)
     rows = jr.sample_base_per_key(keys, n, dim, scale)
     assert rows.shape == (B, n * dim) and np.array_equal(rows[2], jr.sample_base(keys[2], 1, n, dim, scale)[0])
+    # the vectorised per-key pass equals one call per key (odd and even sizes)
+    for size in (39, 8):
+        assert np.array_equal(jr.normal_per_key(keys, size), np.stack([jr.normal(k, (size,)) for k in keys]))
     assert jr.is_key(keys) and jr.is_key(key) and not jr.is_key(7) and not jr.is_key(np.zeros(2, np.float32))
