@@ -14,8 +14,9 @@ jax is not installed here, so this follows the published algorithm of jax's defa
 `_normal_real` = sqrt(2) * erf_inv(uniform(nextafter(-1, 0), 1)); XLA's float32 `ErfInv` polynomial, M. Giles 2010).
 It is PINNED by known answers (tests/test_jax_random.py): the three Random123 / `jax/tests/random_test.py` vectors for
 threefry2x32, `split(PRNGKey(0)) = [[4146024105, 967050713], [2718843009, 1272950319]]`,
-`uniform(PRNGKey(0)) = 0.41845703`, `normal(PRNGKey(0), (1,)) = -0.20584226` and `normal(subkey, (1,)) = -1.2515389`
-(values printed in the JAX documentation, "Sharp Bits" / "Pseudo random numbers").  The last ulp of `normal` depends on
+`uniform(PRNGKey(0)) = 0.41845703`, `normal(PRNGKey(0), (1,)) = -0.20584226`, `normal(subkey, (1,)) = -1.2515389`,
+the ten values of the quickstart's `normal(PRNGKey(0), (10,))` and `normal(PRNGKey(42)) = -0.18471177` (values printed
+in the JAX documentation: quickstart, "Sharp Bits", "Pseudo random numbers").  The last ulp of `normal` depends on
 the libm `log`; XLA:CPU's may differ from numpy's there.
 
 This is the drop-in (key-parity) noise path: numpy on the host, then one H2D copy.  The fast path for large batches

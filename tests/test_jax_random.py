@@ -23,6 +23,11 @@ def test_split_uniform_normal_documented_values():
     assert abs(float(jr.uniform(key)) - 0.41845703) < 1e-8
     assert abs(float(jr.normal(key, (1,))[0]) - (-0.20584226)) < 2e-7
     assert abs(float(jr.normal(sub, (1,))[0]) - (-1.2515389)) < 2e-7
+    # JAX quickstart: x = random.normal(random.PRNGKey(0), (10,)); JAX-101 "Pseudo random numbers": normal(PRNGKey(42))
+    quick = [-0.3721109, 0.26423115, -0.18252768, -0.7368197, -0.44030377, -0.1521442, -0.67135346, -0.5908641,
+             0.73168886, 0.5673026]
+    assert np.abs(jr.normal(key, (10,)) - np.asarray(quick, np.float32)).max() < 2e-7
+    assert abs(float(jr.normal(jr.PRNGKey(42))) - (-0.18471177)) < 2e-7
 
 
 def test_bits_layout_and_ranges():
