@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from ..engine import CnfConfig, Engine, key_to_seed, timestep_frequencies
+from ..utils import jax_random as jr
 from ..nets.egnn import init_flat_params
 from .core import FlowMatchingCNF, optimal_transport_conditional_vf
 
@@ -36,15 +37,21 @@ def build_cnf(n_frames: int, dim: int, sigma_min: float, base_scale: float, n_bl
     def apply(params, positions, time, node_features=None):
         return eng.apply(params, positions, time, node_features)
 
+    def _base(key, n: int):
+        # a jax-style uint32[2] key: the reference's own draw (utils/jax_random.py); an integer seed: the device Philox stream
+        if jr.is_key(key):
+            return torch.from_numpy(jr.sample_base(key, n, cfg.n_frames, cfg.dim, cfg.base_scale)).to(eng.device)
+        return eng.base_sample(key, n)
+
     def sample_base(key, n: int):
-        return eng.base_sample(key, int(n))
+        return _base(key, int(n))
 
     def log_prob_base(x):
         return eng.base_log_prob(x)
 
     def sample_and_log_prob_base(seed, sample_shape=()):
         n = int(np.prod(sample_shape)) if len(tuple(sample_shape)) else 1
-        x = eng.base_sample(seed, n)
+        x = _base(seed, n)
         lp = eng.base_log_prob(x)
         if len(tuple(sample_shape)) == 0:
             return x[0], lp[0]

@@ -22,6 +22,11 @@ def test_jax_keys_reproduce_injected_noise(cuda_device):
     key = jr.PRNGKey(5)
     x_data = np.random.default_rng(0).standard_normal((B, n * dim)).astype(np.float32)
     feat = torch.zeros(B, n, dtype=torch.int32)
+    # cnf.sample_base(key, n) (build_cnf.py:46-61): the reference's draw for a jax key
+    xb = cnf.sample_base(key, 5)
+    assert np.array_equal(xb.cpu().numpy(), jr.sample_base(key, 5, n, dim, 1.5))
+    xs, lps = cnf.sample_and_log_prob_base(key, ())
+    assert np.array_equal(xs.cpu().numpy(), jr.sample_base(key, 1, n, dim, 1.5)[0]) and lps.dim() == 0
     # loss.py:21-24
     x0, t = jr.fm_noise(key, B, n, dim, 1.5)
     l_key, _ = flow_matching_loss_fn(cnf, tree, x_data, key, feat)
