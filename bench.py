@@ -1,19 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the ecnf hot path on B200 (contract in the task statement; metric from BASELINE.json).
 
-Headline workload (BASELINE.json configs[1]): LJ13 (13 particles, 3-D) EGNN CNF, `sample_and_log_prob_cnf` with the
-exact divergence, Dopri5, batch 10 000 per GPU, followed by the LJ target log-density, log-weights and the ESS
-sufficient statistics (setup_training.py:166-185).  One "step" = one such batch.  The solver runs the reference's
-fixed-step branch (use_fixed_step_size=True, dt=0.05 -> exactly 121 vector-field evaluations per trajectory) so the
-work per sample is deterministic and the roofline numerator is exact; parameters are synthetic ('stiffened' init,
-SURVEY 8(d)) because no trained checkpoint exists offline.
+Headline workload (BASELINE.json configs[1], `--workload lj13`, the default): LJ13 (13 particles, 3-D) EGNN CNF,
+`sample_and_log_prob_cnf` with the exact divergence, Dopri5, batch 10 000 per GPU, followed by the LJ target log-density,
+log-weights and the ESS sufficient statistics (setup_training.py:166-185).  One "step" = one such batch.  The solver runs
+the reference's fixed-step branch (use_fixed_step_size=True, dt=0.05 -> exactly 121 vector-field evaluations per
+trajectory) so the work per sample is deterministic and the roofline numerator is exact; parameters are synthetic
+('stiffened' init) because no trained checkpoint exists offline.
 
-Also measured in the same run (reported under "extra"): the QM9-positional flow-matching training step (batch 512,
-BASELINE.json configs[2]) in steps/s.
+Other workloads (each prints one contract line; the default run reports small versions of them under "extra"):
+  --workload aldp    BASELINE configs[3]: ALDP (22 atoms; aldp.yaml net), sample + exact log q + log-weights + ESS,
+                     100 000 trajectories over the N GPUs with --scaling strong (12 500 per GPU with weak).  The reference
+                     has no ALDP energy (examples/aldp.py:42-49 passes no target_log_prob_fn): log p is the LJ-style
+                     energy of leonard_jones.py:10-27 on the 22 atoms -- a stand-in, stated here and in DESIGN.md.
+  --workload dw4     BASELINE configs[0]: DW4, batch 1024, sample + exact log q.
+  --workload sweep   BASELINE configs[4]: LJ13 `sample_cnf` (no divergence; load_checkpoint_measure_sampling_time.py:
+                     101-119), global batch 1k / 10k / 100k / 1M split over the N GPUs.
+  --workload fm      BASELINE configs[2]: QM9-positional flow-matching training step, batch 512 per GPU.
+--scaling strong splits a fixed global batch over the ranks (default: weak, per-GPU batch fixed).
 
-`--impl reference` times the CPU restatement of the reference (oracle/, torch fp32, reverse-mode Jacobian exactly
-like sample_and_log_prob.py:64-66) on the host cores: JAX is not installable in this image, so the reference itself
-cannot run ("reference arm").
+`--impl reference` times the CPU restatement of the reference (oracle/, torch fp32, reverse-mode Jacobian exactly like
+sample_and_log_prob.py:64-66) on the host cores: JAX is not installable in this image, so the reference itself cannot
+run ("reference arm").  That arm never touches the CUDA library.
 """
 from __future__ import annotations
 
@@ -34,11 +42,14 @@ sys.path.insert(0, ROOT)
 
 LJ13 = dict(n_frames=13, dim=3, sigma_min=0.01, base_scale=1.0, n_blocks_egnn=3, mlp_units=(128, 128, 128),
             n_invariant_feat_hidden=64, time_embedding_dim=8, n_features=1)
+DW4 = dict(n_frames=4, dim=2, sigma_min=0.01, base_scale=1.0, n_blocks_egnn=3, mlp_units=(128, 128, 128),
+           n_invariant_feat_hidden=64, time_embedding_dim=8, n_features=1)
 QM9 = dict(n_frames=19, dim=3, sigma_min=1e-6, base_scale=2.0, n_blocks_egnn=5, mlp_units=(256, 256, 256, 256),
            n_invariant_feat_hidden=32, time_embedding_dim=8, n_features=1)
+ALDP = dict(n_frames=22, dim=3, sigma_min=1e-6, base_scale=0.2, n_blocks_egnn=3, mlp_units=(64, 64),
+            n_invariant_feat_hidden=32, time_embedding_dim=8, n_features=22)
+CFGS = {"lj13": LJ13, "dw4": DW4, "qm9": QM9, "aldp": ALDP}
 N_EVALS_FIXED = 121          # 1 FSAL init + 6 stages x 20 steps (dt = 0.05)
-# one ncu --set full capture of ecnf_solve_tc_kernel (profiles/r1_solve_tc_full.txt): dram read + write bytes per trajectory
-NCU_DRAM_BYTES_PER_TRAJ = (19.957129e9 + 43.069807e9) / 148   # ncu --set full, 148 trajectories (profiles/r1_solve_tc_full.txt)
 METRIC = "LJ13 samples/s with exact log-q (Dopri5)"
 UNIT = "samples/s"
 
@@ -58,6 +69,17 @@ def peaks():
         d = json.load(open(p))
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def ncu_traffic(kernel_key: str):
+    """dram bytes per trajectory of the dominant kernel from the committed ncu capture (profiles/r2_traffic.json): a
+    SEPARATE capture of the same kernel, not measured in this run -- the line says so."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p)).get(kernel_key)
+        if d:
+            return d["dram_bytes_per_trajectory"], d["source"]
+    return None, None
 
 
 class ClockSampler:
@@ -104,45 +126,74 @@ class ClockSampler:
             for nm, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        # the busiest half of the samples = "under load"
-        sm_sorted = sorted(sm)
+        sm_sorted = sorted(sm)       # the busiest half of the samples = "under load"
         return {"sm_mhz": statistics.median(sm_sorted[len(sm_sorted) // 2:]) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU legs (the only place bench.py touches oracle/)
+# CPU legs (the only place bench.py touches oracle/; they never load libecnf_b200.so)
 # ----------------------------------------------------------------------------------------------------------
-def cpu_sample_logq(flat_params: dict, n_traj: int, threads: int, seed: int = 2):
-    """Time `n_traj` LJ13 trajectories of sample_and_log_prob (exact, fixed dt=0.05) on the host cores."""
+def host_params(name: str, seed: int = 0, head_variance: float = 1.0) -> dict:
+    """The GPU arm's synthetic parameters as {flax path: array}, built from the oracle's layout: no Engine, no .so."""
+    from oracle import ecnf_oracle as O
+    from ecnf_b200.nets.egnn import init_param_tensors
+    return init_param_tensors(O.param_layout(O.CnfConfig(**CFGS[name])), seed, head_variance)
+
+
+def cpu_sample_logq(name: str, params: dict, n_traj: int, threads: int, seed: int = 2, div: bool = True):
+    """Time `n_traj` trajectories of sample_and_log_prob (exact, fixed dt=0.05) -- or sample_cnf -- on the host cores."""
     from oracle import ecnf_oracle as O
     torch.set_num_threads(threads)
     torch.set_flush_denormal(True)
-    ocfg = O.CnfConfig(**LJ13)
-    p = O.to_torch(flat_params, torch.float32)
+    ocfg = O.CnfConfig(**CFGS[name])
+    p = O.to_torch(params, torch.float32)
     rng = np.random.default_rng(seed)
     x0 = O.base_sample_from_noise(ocfg, torch.tensor(rng.standard_normal((n_traj, ocfg.D)), dtype=torch.float32))
-    feat = torch.zeros(n_traj, ocfg.n_frames, dtype=torch.long)
+    feat = torch.arange(ocfg.n_frames).remainder(ocfg.n_features).repeat(n_traj, 1)
     t0 = time.perf_counter()
-    x1, logq, st = O.sample_and_log_prob_cnf(p, ocfg, x0, feat, O.SolveControl(fixed=True, step_size=0.05))
-    lw = -O.lj_energy(x1.numpy().reshape(n_traj, 13, 3).astype(np.float64)) - logq.numpy()
-    O.reverse_ess(lw)
+    if div:
+        x1, logq, st = O.sample_and_log_prob_cnf(p, ocfg, x0, feat, O.SolveControl(fixed=True, step_size=0.05))
+        if name != "dw4":
+            lw = -O.lj_energy(x1.numpy().reshape(n_traj, ocfg.n_frames, ocfg.dim).astype(np.float64)) - logq.numpy()
+        else:
+            lw = -O.dw_energy(x1.numpy().reshape(n_traj, ocfg.n_frames, ocfg.dim).astype(np.float64)) - logq.numpy()
+        O.reverse_ess(lw)
+    else:
+        x1, st = O.sample_cnf(p, ocfg, x0, feat, O.SolveControl(fixed=True, step_size=0.05))
     dt = time.perf_counter() - t0
     assert int(st.n_evals[0]) == N_EVALS_FIXED
     return n_traj / dt, dt
 
 
-def synthetic_params_numpy(cfg: dict, seed: int = 0, head_variance: float = 1.0) -> dict:
-    """Same synthetic parameters as the GPU arm, as a {flax path: array} dict, without touching CUDA."""
-    from ecnf_b200.engine import CnfConfig, Engine
-    from ecnf_b200.nets.egnn import init_flat_params
-    eng = Engine(CnfConfig(**cfg))
-    flat = init_flat_params(eng, seed, head_variance)
-    out = {}
-    for path, off, shape in eng.layout:
-        cnt = int(np.prod(shape)) if shape else 1
-        out[path] = flat[off:off + cnt].reshape(shape).copy()
-    return out, eng, flat
+def cpu_fm_steps(B: int, steps: int, threads: int):
+    """QM9-positional FM step on the host cores: oracle loss + autograd gradient + restated Adam/EMA
+    (gradient_step.py:20-53), `steps` steps at batch B."""
+    from oracle import ecnf_oracle as O
+    torch.set_num_threads(threads)
+    ocfg = O.CnfConfig(**QM9)
+    flat = host_params("qm9", 0, 0.001)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((B, 19, 3)).astype(np.float32) * 1.5
+    x = torch.tensor((x - x.mean(axis=1, keepdims=True)).reshape(B, 57))
+    feat = torch.zeros(B, 19, dtype=torch.long)
+    m = {k: np.zeros_like(v) for k, v in flat.items()}
+    v2 = {k: np.zeros_like(v) for k, v in flat.items()}
+    ema = {k: v.copy() for k, v in flat.items()}
+    t0 = time.perf_counter()
+    for s in range(steps):
+        x0 = O.base_sample_from_noise(ocfg, torch.tensor(rng.standard_normal((B, 57)), dtype=torch.float32))
+        t = torch.tensor(rng.uniform(0, 1, B), dtype=torch.float32)
+        loss, g = O.fm_loss_and_grad(flat, ocfg, x, x0, t, feat, dtype=torch.float32)
+        for k in flat:
+            p_, m_, v_, _ = O.adam_step(flat[k], g[k].numpy(), m[k], v2[k], s, 1e-4)
+            flat[k], m[k], v2[k] = p_.astype(np.float32), m_.astype(np.float32), v_.astype(np.float32)
+            ema[k] = 0.999 * ema[k] + 0.001 * flat[k]
+    dt = time.perf_counter() - t0
+    return steps / dt, dt, float(loss)
+
+
+CPU_TRAJ = 4     # trajectories per CPU step: the SAME bounded sample in the reference arm and in cpu_baseline
 
 
 def run_reference(args):
@@ -150,26 +201,24 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    params, _, _ = synthetic_params_numpy(LJ13)
-    budget = 200.0 / max(1, args.steps + args.warmup)        # seconds per step
-    # calibrate: one small solve tells the per-trajectory cost
-    _, t2 = cpu_sample_logq(params, 2, threads)
-    n_traj = int(max(1, min(64, (budget / (t2 / 2)) * 0.7)))
-    for _ in range(args.warmup):
-        cpu_sample_logq(params, n_traj, threads)
+    params = host_params("lj13")
     times = []
+    for _ in range(max(0, min(args.warmup, 1))):          # torch-CPU has no compile step: one warm-up pass is enough
+        cpu_sample_logq("lj13", params, CPU_TRAJ, threads)
     for _ in range(args.steps):
-        _, dt = cpu_sample_logq(params, n_traj, threads)
+        _, dt = cpu_sample_logq("lj13", params, CPU_TRAJ, threads)
         times.append(dt)
-    value = n_traj * len(times) / sum(times)
+        if sum(times) > 240.0:
+            break
+    value = CPU_TRAJ * len(times) / sum(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "lj13_sample_and_log_prob_exact_dopri5_fixed_dt0.05+lj_log_weights+ess", "batch_per_step": n_traj,
-                   "n_evals_per_sample": N_EVALS_FIXED},
+        "config": {"workload": "lj13_sample_and_log_prob_exact_dopri5_fixed_dt0.05+lj_log_weights+ess", "batch_per_step": CPU_TRAJ,
+                   "n_evals_per_sample": N_EVALS_FIXED, "params": "synthetic stiffened init (seed 0), same as the GPU arm"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_traj} LJ13 trajectories per step (121 evals each), torch-CPU fp32 restatement "
+                         "sample": f"{CPU_TRAJ} LJ13 trajectories per step (121 evals each), torch-CPU fp32 restatement "
                                    "of the reference with reverse-mode Jacobian; the JAX reference cannot be installed "
                                    "in this image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -179,260 +228,460 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=10_000, help="trajectories per GPU per step")
-    ap.add_argument("--no-train", action="store_true", help="skip the secondary QM9 training-step measurement")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline")
-    ap.add_argument("--adaptive", action="store_true", help="PID-controlled steps (rtol=atol=1e-5) instead of dt=0.05")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def count_kernels(fn):
+    """(our kernels, other kernels) launched by fn(), counted from CUPTI activity records (torch.profiler sees every kernel
+    of the process, including those of libecnf_b200.so).  None when the profiler is unavailable."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        ours = others = 0
+        names = {}
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) != torch.autograd.DeviceType.CUDA:
+                continue
+            nm = ev.name
+            if nm.startswith("Memcpy") or nm.startswith("Memset"):
+                continue
+            if "at::" in nm or "cub::" in nm or "nccl" in nm.lower() or "cutlass" in nm or "cublas" in nm.lower():
+                others += 1
+            else:
+                ours += 1
+                key = nm.split("(")[0][-60:]
+                names[key] = names.get(key, 0) + 1
+        return ours, others, names
+    except Exception as e:  # noqa: BLE001
+        return None, None, {"error": repr(e)}
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+class Ctx:
+    pass
+
+
+def setup(args):
+    c = Ctx()
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(c.local_rank)
+    c.dev = torch.device("cuda", c.local_rank)
     import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    c.dist = dist
+    if c.world > 1:
+        dist.init_process_group("nccl", device_id=c.dev)
+    c.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=c.dev)   # > 126 MB L2
+    return c
 
-    from ecnf_b200 import lib as L
+
+def barrier(c):
+    if c.world > 1:
+        c.dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(c, ms: float) -> float:
+    t = torch.tensor([ms], dtype=torch.float64, device=c.dev)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return t.item()
+
+
+def sum_over_ranks(c, v: float) -> float:
+    t = torch.tensor([v], dtype=torch.float64, device=c.dev)
+    if c.world > 1:
+        c.dist.all_reduce(t, op=c.dist.ReduceOp.SUM)
+    return t.item()
+
+
+def make_model(c, name: str, head_variance: float = 1.0):
     from ecnf_b200.cnf import build_cnf
-    from ecnf_b200.engine import PackedParams, ess_from_stats
+    from ecnf_b200.engine import PackedParams
     from ecnf_b200.nets.egnn import init_flat_params
-    from ecnf_b200.distributed import merge_ess_stats
-
-    cnf = build_cnf(**LJ13)
+    cnf = build_cnf(**CFGS[name])
     eng = cnf.engine
-    flat_host = init_flat_params(eng, 0, head_variance=1.0)
-    params = PackedParams(torch.from_numpy(flat_host).to(dev))
-    B = args.batch
-    goff = rank * B                                      # noise keyed by GLOBAL sample index
-    feat = torch.zeros(B, 13, dtype=torch.int32, device=dev)
-    ctrl = L.make_ctrl(use_fixed_step_size=not args.adaptive)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    params = PackedParams(torch.from_numpy(init_flat_params(eng, 0, head_variance=head_variance)).to(c.dev))
+    return cnf, eng, params
 
+
+def shard(c, global_batch: int):
+    from ecnf_b200.distributed import shard_range
+    return shard_range(global_batch, c.rank, c.world)
+
+
+def bench_solve(c, name: str, b_begin: int, b_end: int, *, div: bool, adaptive: bool, steps: int, warmup: int,
+                target: int | None, e2e_steps: int = 0, sample_clocks: bool = False, count: bool = True):
+    """Times `steps` passes of sample(+exact log q)(+target log-density, log-weights, ESS statistics) over the global
+    sample indices [b_begin, b_end) of this rank.  Returns a dict with device-timed throughput (max over ranks), the
+    solve kernel's own time, evaluation counts, the end-to-end (host buffers) figure and the launch count."""
+    from ecnf_b200 import lib as L
+    from ecnf_b200.cnf import sample_and_log_prob_cnf, sample_cnf
+    from ecnf_b200.distributed import merge_ess_stats
+    from ecnf_b200.engine import ess_from_stats
+    cfg = CFGS[name]
+    cnf, eng, params = make_model(c, name)
+    n, D = cfg["n_frames"], cfg["n_frames"] * cfg["dim"]
+    B = b_end - b_begin
+    feat = (torch.arange(n, dtype=torch.int32, device=c.dev) % cfg["n_features"]).repeat(B, 1).contiguous()
+    ctrl = L.make_ctrl(use_fixed_step_size=not adaptive)
+    mode = L.MODE_SAMPLE_LOGQ if div else L.MODE_SAMPLE
     kernel_events = []
 
     def step_resident(x0, timed=False):
         if timed:
             ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ka.record()
-        x1, logs, stats = eng.solve(params, L.MODE_SAMPLE_LOGQ, x0, feat, ctrl)
+        x1, logs, stats = eng.solve(params, mode, x0, feat, ctrl)
         if timed:
             kb.record()
             kernel_events.append((ka, kb))
-        log_w = eng.target_log_prob(L.TARGET_LJ, x1) - logs[:, 0]
-        st = eng.ess_stats(log_w)
-        if world > 1:
-            st = merge_ess_stats(st)
+        st = None
+        if div and target is not None:
+            log_w = eng.target_log_prob(target, x1) - logs[:, 0]
+            st = eng.ess_stats(log_w)
+            if c.world > 1:
+                st = merge_ess_stats(st)
         return x1, logs, stats, st
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    x0_res = eng.base_sample(2, B, goff)
-    for _ in range(args.warmup):
+    x0_res = eng.base_sample(2, B, b_begin)               # noise keyed by GLOBAL sample index
+    for _ in range(warmup):
         step_resident(x0_res)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    n_evals_total = 0
-    for i in range(args.steps):
-        flush.zero_()
-        barrier()
+    barrier(c)
+    sampler = None
+    if sample_clocks:
+        sampler = ClockSampler(c.local_rank)
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    evals_last = 0
+    bad = 0
+    for i in range(steps):
+        c.flush.zero_()
+        barrier(c)
         ev[i][0].record()
         x1, logs, stats, st = step_resident(x0_res, timed=True)
         ev[i][1].record()
-        barrier()
-        n_evals_total += int(stats[:, 2].sum().item())
-    t_steps = [a.elapsed_time(b) for a, b in ev]                       # ms, per step
-    t_total = torch.tensor([sum(t_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
-    value = world * B * args.steps / (t_total.item() * 1e-3)
-    ms_per_step = t_total.item() / args.steps
+        barrier(c)
+        evals_last = int(stats[:, 2].sum().item())
+        bad += int((stats[:, 3] != 0).sum().item())
+    t_steps = [a.elapsed_time(b) for a, b in ev]
+    total_ms = max_over_ranks(c, sum(t_steps))
+    clocks = sampler.stop() if sampler else None
+    global_B = int(sum_over_ranks(c, B))
+    k_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / len(kernel_events)
+    out = {"value": global_B * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "kernel_ms": k_ms,
+           "evals_per_launch": evals_last, "batch_this_rank": B, "global_batch": global_B, "step_ms": t_steps,
+           "clocks": clocks, "status_failures": bad, "eng": eng, "D": D}
+    if st is not None:
+        rv, fw = ess_from_stats(st.tolist(), global_B)
+        out["reverse_ess"], out["forward_ess"] = rv, fw
 
-    # ---- dominant kernel (the persistent solve kernel), CUDA events on its launch stream inside the timed steps
-    k_times = [a.elapsed_time(b) for a, b in kernel_events]
-    kstats = stats
-    clocks = sampler.stop()
-    k_ms = sum(k_times) / len(k_times)
-    evals_per_launch = int(kstats[:, 2].sum().item())
-    f_fwd = fwd_flops(LJ13)
-    alg_flops = evals_per_launch * (1 + 39) * f_fwd                    # (1 + D) * F_fwd per eval
-    pk, pk_kind = peaks()
-    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])      # the kernel runs for seconds: sustained figure
-    achieved_tf = alg_flops / (k_ms * 1e-3) / 1e12
+    launches_per_step = None
+    if count:
+        ours, others, names = count_kernels(lambda: step_resident(x0_res))
+        out["kernels_per_step"] = {"ours": ours, "torch_or_library": others, "by_name": names}
+        launches_per_step = ours
+    out["launches_per_step"] = launches_per_step if launches_per_step is not None else 1
 
-    # ---- end to end through the public API with host buffers (H2D of the noise + features, D2H of the results)
-    from ecnf_b200.cnf import sample_and_log_prob_cnf
-    rng = np.random.default_rng(1000 + rank)
-    eps_host = torch.from_numpy(rng.standard_normal((B, 39)).astype(np.float32)).pin_memory()
-    feat_host = torch.zeros(B, 13, dtype=torch.int32).pin_memory()
-    out_x = torch.empty(B, 39, dtype=torch.float32).pin_memory()
-    out_lq = torch.empty(B, dtype=torch.float32).pin_memory()
-    out_ess = torch.empty(5, dtype=torch.float32).pin_memory()
+    if e2e_steps > 0:
+        # end to end through the public API with HOST buffers: H2D of noise + features, D2H of samples, log q, ESS stats
+        rng = np.random.default_rng(1000 + c.rank)
+        eps_host = torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32)).pin_memory()
+        feat_host = feat.cpu().pin_memory()
+        out_x = torch.empty(B, D, dtype=torch.float32).pin_memory()
+        out_lq = torch.empty(B, dtype=torch.float32).pin_memory()
+        out_ess = torch.empty(5, dtype=torch.float32).pin_memory()
 
-    def step_e2e():
-        eps = eps_host.to(dev, non_blocking=True)
-        f = feat_host.to(dev, non_blocking=True)
-        x0 = eng.base_sample_from_noise(eps)
-        x1, log_q = sample_and_log_prob_cnf(cnf, params, None, f, use_fixed_step_size=not args.adaptive, x0=x0)
-        log_w = eng.target_log_prob(L.TARGET_LJ, x1) - log_q
-        st = eng.ess_stats(log_w)
-        if world > 1:
-            st = merge_ess_stats(st)
-        out_x.copy_(x1, non_blocking=True)
-        out_lq.copy_(log_q, non_blocking=True)
-        out_ess.copy_(st, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        def step_e2e():
+            eps = eps_host.to(c.dev, non_blocking=True)
+            f = feat_host.to(c.dev, non_blocking=True)
+            x0 = eng.base_sample_from_noise(eps)
+            if div:
+                x1, log_q = sample_and_log_prob_cnf(cnf, params, None, f, use_fixed_step_size=not adaptive, x0=x0,
+                                                    check_status=False)
+                out_lq.copy_(log_q, non_blocking=True)
+                if target is not None:
+                    st_ = eng.ess_stats(eng.target_log_prob(target, x1) - log_q)
+                    if c.world > 1:
+                        st_ = merge_ess_stats(st_)
+                    out_ess.copy_(st_, non_blocking=True)
+            else:
+                x1 = sample_cnf(cnf, params, None, f, use_fixed_step_size=not adaptive, x0=x0, check_status=False)
+            out_x.copy_(x1, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
-    e2e_steps = max(1, min(args.steps, 2))
-    barrier()
-    t0 = time.perf_counter()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(e2e_steps):
         step_e2e()
-    b.record()
-    barrier()
-    e2e_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / (e2e_ms.item() * 1e-3)
-    rv_ess, fw_ess = ess_from_stats(out_ess.tolist(), world * B)
-
-    # ---- secondary: QM9-positional flow-matching training step, batch 512 per GPU (weak scaling)
-    extra = {}
-    launches = args.steps * 3 + e2e_steps * 4
-    if not args.no_train:
-        # ---- secondary: plain sampling without a divergence (sample_cnf; BASELINE.json configs[4], the reference's
-        #      load_checkpoint_measure_sampling_time.py path), LJ13, 4736 trajectories per GPU, device-resident noise
-        Bs = min(B, 148 * 32)
-        eng.solve(params, L.MODE_SAMPLE, x0_res[:Bs], feat[:Bs], ctrl)
-        barrier()
-        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sa.record()
-        eng.solve(params, L.MODE_SAMPLE, x0_res[:Bs], feat[:Bs], ctrl)
-        sb.record()
-        barrier()
-        s_ms = torch.tensor([sa.elapsed_time(sb)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(s_ms, op=dist.ReduceOp.MAX)
-        extra["sample_only"] = {"metric": "LJ13 sample_cnf samples/s (no divergence, Dopri5 " + ("adaptive" if args.adaptive else "dt=0.05") + ")",
-                                "value": world * Bs / (s_ms.item() * 1e-3), "unit": "samples/s", "batch_per_gpu": Bs,
-                                "ms": s_ms.item()}
-        launches += 2 * 3
-        extra["fm_train"] = bench_train(args, dev, rank, world)
-        launches += extra["fm_train"].pop("_launches")
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        p_np, _, _ = synthetic_params_numpy(LJ13)
-        threads = os.cpu_count() or 1
-        v, dt = cpu_sample_logq(p_np, 4, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"4 LJ13 trajectories x 121 evals (fixed dt=0.05) in {dt:.1f} s, torch-CPU fp32 restatement of "
-                         "the reference (reverse-mode Jacobian); JAX reference not installable here"}
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "lj13_sample_and_log_prob_exact_dopri5_" + ("adaptive_rtol1e-5" if args.adaptive else "fixed_dt0.05")
-                                   + "+lj_log_weights+ess", "batch_per_gpu": B, "global_batch": world * B,
-                       "n_evals_per_sample": evals_per_launch / B, "params": "synthetic stiffened init (seed 0)",
-                       "l2": "256 MiB flush buffer written between timed steps", "parallelism": f"dp{world} (independent trajectories; ESS statistics all-gathered)"},
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_TRAJ * B if NCU_DRAM_BYTES_PER_TRAJ else None,
-                         "kernel": "ecnf_solve_tc_kernel (tcgen05 + TMEM, 3-pass bf16 split, fp32 accumulate)",
-                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": alg_flops,
-                         "executed_tensor_flops_per_launch": evals_per_launch * int(eng.lib.ecnf_solve_tensor_flops_per_eval(eng.handle)),
-                         "peak_source": f"{pk_kind} bf16 dense sustained (MEASURED_PEAKS.json); numerator = algorithmic "
-                                        "(1+D)*F_fwd per evaluation (SURVEY 8(d)); the kernel executes 3 bf16 passes over "
-                                        "a structurally reduced tangent set, see executed_tensor_flops_per_launch",
-                         "traffic_source": "profiles/r1_solve_tc_full.txt: dram bytes of one ncu --set full capture, per trajectory x batch"},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 39 * 4 + B * 13 * 4,
-                    "d2h_bytes_per_step": B * 39 * 4 + B * 4 + 20},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "extra": {**extra, "reverse_ess": rv_ess, "forward_ess": fw_ess, "step_ms": t_steps},
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        barrier(c)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            step_e2e()
+        b.record()
+        barrier(c)
+        e2e_ms = max_over_ranks(c, a.elapsed_time(b))
+        out["e2e"] = {"value": global_B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "steps": e2e_steps,
+                      "h2d_bytes_per_step": B * D * 4 + B * n * 4,
+                      "d2h_bytes_per_step": B * D * 4 + (B * 4 if div else 0) + (20 if div and target is not None else 0)}
+    return out
 
 
-def bench_train(args, dev, rank, world):
-    """QM9-positional FM training step (loss + grad + all-reduce + Adam/EMA), batch 512 per GPU."""
-    import torch.distributed as dist
-    from ecnf_b200.cnf import build_cnf, flow_matching_update_fn, TrainingState
-    from ecnf_b200.engine import PackedParams
-    from ecnf_b200.nets.egnn import init_flat_params
-    from ecnf_b200.utils.optim import Adam, warmup_cosine_decay_schedule
+def roofline_of(c, name: str, r: dict, div: bool):
+    cfg = CFGS[name]
+    D = cfg["n_frames"] * cfg["dim"]
+    f_eval = ((1 + D) if div else 1) * fwd_flops(cfg)                # SURVEY 8(d): (1 + D) * F_fwd per exact-div evaluation
+    alg = r["evals_per_launch"] * f_eval
+    pk, pk_kind = peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) if r["kernel_ms"] > 1000 else pk["bf16_tflops"]
+    tf = alg / (r["kernel_ms"] * 1e-3) / 1e12
+    eng = r["eng"]
+    tc_flops = int(eng.lib.ecnf_solve_tensor_flops_per_eval(eng.handle)) if div else 0
+    per_traj, src = ncu_traffic(("solve_tc_" if tc_flops else "solve_simt_") + name)
+    return {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+            "traffic": per_traj * r["batch_this_rank"] if per_traj else None,
+            "kernel": ("ecnf_solve_tc_kernel (tcgen05 + TMEM, 3-pass bf16 split, fp32 accumulate)" if tc_flops or not div
+                       else "ecnf_solve_kernel (fp32 SIMT)"),
+            "kernel_ms": r["kernel_ms"], "algorithmic_flops_per_launch": alg,
+            "executed_tensor_flops_per_launch": r["evals_per_launch"] * tc_flops if tc_flops else None,
+            "peak_source": f"{pk_kind} bf16 dense {'sustained' if r['kernel_ms'] > 1000 else 'burst'} (MEASURED_PEAKS.json); "
+                           "numerator = algorithmic (1+D)*F_fwd per evaluation (SURVEY 8(d)); the kernel executes 3 bf16 "
+                           "passes over a structurally reduced tangent set, see executed_tensor_flops_per_launch",
+            "traffic_source": (src + " -- a separate ncu capture of this kernel, NOT measured in this run") if src else None}
+
+
+def bench_train(c, *, steps: int = 10, cpu: bool = False):
+    """QM9-positional FM training step (loss + grad + all-reduce + Adam/EMA), batch 512 per GPU; every step copies its
+    batch from pinned host memory and reads the loss back (the e2e figure IS the figure)."""
+    from ecnf_b200.cnf import flow_matching_update_fn, TrainingState
     from ecnf_b200.distributed import make_grad_allreduce
-    cnf = build_cnf(**QM9)
-    eng = cnf.engine
+    from ecnf_b200.utils.optim import Adam, warmup_cosine_decay_schedule
+    cnf, eng, params = make_model(c, "qm9", head_variance=0.001)
     B = 512
-    params = PackedParams(torch.from_numpy(init_flat_params(eng, 0)).to(dev))
     opt = Adam(warmup_cosine_decay_schedule(1e-4, 1e-4, 10, 100_000, 0.0))
-    state = TrainingState(params=params, opt_state=opt.init(params), key=rank, ema_params=params)
-    rng = np.random.default_rng(3 + rank)
+    state = TrainingState(params=params, opt_state=opt.init(params), key=c.rank, ema_params=params)
+    rng = np.random.default_rng(3 + c.rank)
     x = rng.standard_normal((B, 19, 3)).astype(np.float32) * 1.5
     x = (x - x.mean(axis=1, keepdims=True)).reshape(B, 57)
     x_host = torch.from_numpy(x).pin_memory()
     feat_host = torch.zeros(B, 19, dtype=torch.int32).pin_memory()
-    hook = make_grad_allreduce(world) if world > 1 else None
-    denom = float(world * B * 57)
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    hook = make_grad_allreduce(c.world) if c.world > 1 else None
+    denom = float(c.world * B * 57)
 
-    def step(st):
-        xd = x_host.to(dev, non_blocking=True)
-        fd = feat_host.to(dev, non_blocking=True)
+    def step(st, read_loss):
+        xd = x_host.to(c.dev, non_blocking=True)
+        fd = feat_host.to(c.dev, non_blocking=True)
         st, info = flow_matching_update_fn(cnf, opt.update, st, xd, fd, grad_allreduce=hook,
-                                           global_offset=rank * B, loss_denominator=denom)
+                                           global_offset=c.rank * B, loss_denominator=denom)
+        if read_loss:
+            loss_host.copy_(info["loss"].reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         return st, info
 
     for _ in range(3):
-        state, info = step(state)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    K = 10
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(K):
-        state, info = step(state)
-    loss = float(info["loss"])          # D2H read of the step's metric
-    b.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = ms.item() / K
+        state, info = step(state, True)
+    barrier(c)
+    res = {}
+    for label, read_loss in (("resident", False), ("e2e", True)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            state, info = step(state, read_loss)
+        b.record()
+        barrier(c)
+        res[label] = max_over_ranks(c, a.elapsed_time(b)) / steps
+    loss = float(info["loss"])
+    holder = {"s": state}
+
+    def one():
+        holder["s"], _ = step(holder["s"], True)
+    ours, others, names = count_kernels(one)
     flops = 3.0 * fwd_flops(QM9) * B                     # per GPU (weak scaling: every rank steps its own 512 graphs)
-    pk, _ = peaks()
-    tf = flops / (ms_step * 1e-3) / 1e12
-    return {"metric": "QM9-positional FM train steps/s (batch 512 per GPU, loss+grad+Adam+EMA, H2D of the batch inside)",
-            "value": 1e3 / ms_step, "unit": "steps/s", "ms_per_step": ms_step, "loss": loss,
-            "global_batch": B * world, "graphs_per_s": B * world * 1e3 / ms_step,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
-                         "unit": "TFLOP/s", "frac": tf / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
-                         "algorithmic_flops_per_step": flops, "per": "GPU"},
-            "_launches": 13 * 360}
+    pk, pk_kind = peaks()
+    peak = pk["bf16_tflops"]                              # a 10-20 ms step: burst figure
+    tf = flops / (res["resident"] * 1e-3) / 1e12
+    out = {"metric": "QM9-positional FM train steps/s (batch 512 per GPU, loss+grad+Adam+EMA, H2D of the batch inside)",
+           "value": 1e3 / res["resident"], "unit": "steps/s", "ms_per_step": res["resident"], "loss": loss,
+           "global_batch": B * c.world, "graphs_per_s": B * c.world * 1e3 / res["resident"],
+           "e2e": {"value": 1e3 / res["e2e"], "unit": "steps/s", "h2d_bytes_per_step": B * 57 * 4 + B * 19 * 4,
+                   "d2h_bytes_per_step": 4, "note": "+ a device->host read of the loss every step"},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                        "algorithmic_flops_per_step": flops, "per": "GPU", "peak_source": f"{pk_kind} bf16 dense burst"},
+           "kernels_per_step": {"ours": ours, "torch_or_library": others}, "launches_per_step": ours or 1}
+    if cpu and c.rank == 0 and c.world == 1:
+        threads = os.cpu_count() or 1
+        v, dt, l_cpu = cpu_fm_steps(B, 3, threads)
+        out["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+                               "sample": f"3 steps at batch {B} in {dt:.1f} s: oracle loss + torch autograd gradient + restated "
+                                         "Adam/EMA (gradient_step.py:20-53), torch-CPU fp32"}
+    return out
+
+
+def contract_line(c, args, *, metric, unit, r, workload, cfg_extra, roofline, cpu, extra, scaling, launches):
+    return {
+        "metric": metric, "value": r["value"], "unit": unit, "n_gpus": c.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "params": "synthetic stiffened init (seed 0)",
+                   "l2": "256 MiB flush buffer written between timed steps", **cfg_extra},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": r.get("e2e"), "gpu_launches": launches, "clocks": r.get("clocks"),
+        "extra": extra,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lj13", choices=["lj13", "aldp", "dw4", "sweep", "fm"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=None, help="trajectories per GPU (weak) or in total (strong) per step")
+    ap.add_argument("--no-extra", "--no-train", dest="no_extra", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baselines")
+    ap.add_argument("--adaptive", action="store_true", help="PID-controlled steps (rtol=atol=1e-5) instead of dt=0.05")
+    ap.add_argument("--sweep-max", type=int, default=1_000_000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    c = setup(args)
+    from ecnf_b200 import lib as L
+    strong = args.scaling == "strong"
+
+    def rng_for(default_per_gpu, default_total):
+        if strong:
+            return shard(c, args.batch or default_total)
+        b = args.batch or default_per_gpu
+        return c.rank * b, (c.rank + 1) * b
+
+    par = (f"dp{c.world} (independent trajectories, " + ("fixed global batch split over ranks" if strong else "fixed per-GPU batch")
+           + "; ESS statistics all-gathered)")
+    fixed_tag = "adaptive_rtol1e-5" if args.adaptive else "fixed_dt0.05"
+    line = None
+
+    if args.workload == "lj13":
+        b0, b1 = rng_for(10_000, 10_000)
+        r = bench_solve(c, "lj13", b0, b1, div=True, adaptive=args.adaptive, steps=args.steps, warmup=args.warmup,
+                        target=L.TARGET_LJ, e2e_steps=max(1, min(args.steps, 3)), sample_clocks=True)
+        extra = {"reverse_ess": r.get("reverse_ess"), "forward_ess": r.get("forward_ess"), "step_ms": r["step_ms"],
+                 "kernels_per_step": r.get("kernels_per_step"), "status_failures": r["status_failures"]}
+        launches = r["launches_per_step"] * args.steps
+        if not args.no_extra:
+            ra = bench_solve(c, "lj13", c.rank * 2368, (c.rank + 1) * 2368, div=True, adaptive=True, steps=1, warmup=1,
+                             target=L.TARGET_LJ, count=False)
+            extra["lj13_adaptive"] = {"metric": "LJ13 samples/s with exact log-q (Dopri5 adaptive rtol=atol=1e-5, the reference's shipped setting)",
+                                      "value": ra["value"], "unit": UNIT, "batch_per_gpu": 2368,
+                                      "evals_per_sample": ra["evals_per_launch"] / 2368, "roofline": roofline_of(c, "lj13", ra, True),
+                                      "status_failures": ra["status_failures"]}
+            rd = bench_solve(c, "dw4", c.rank * 1024, (c.rank + 1) * 1024, div=True, adaptive=False, steps=2, warmup=1,
+                             target=L.TARGET_DW, e2e_steps=2, count=False)
+            extra["dw4"] = {"metric": "DW4 samples/s with exact log-q (batch 1024, dt=0.05) + DW log-weights + ESS",
+                            "value": rd["value"], "unit": UNIT, "e2e": rd["e2e"], "roofline": roofline_of(c, "dw4", rd, True)}
+            rl = bench_solve(c, "aldp", c.rank * 1184, (c.rank + 1) * 1184, div=True, adaptive=False, steps=1, warmup=1,
+                             target=L.TARGET_LJ, e2e_steps=1, count=False)
+            extra["aldp"] = {"metric": "ALDP samples/s with exact log-q (batch 1184 per GPU, dt=0.05) + stand-in LJ log-weights + ESS",
+                             "value": rl["value"], "unit": UNIT, "e2e": rl["e2e"], "roofline": roofline_of(c, "aldp", rl, True)}
+            rs = bench_solve(c, "lj13", c.rank * 4736, (c.rank + 1) * 4736, div=False, adaptive=args.adaptive, steps=1, warmup=1,
+                             target=None, e2e_steps=1, count=False)
+            extra["sample_only"] = {"metric": f"LJ13 sample_cnf samples/s (no divergence, Dopri5 {fixed_tag})", "value": rs["value"],
+                                    "unit": UNIT, "batch_per_gpu": 4736, "e2e": rs["e2e"], "roofline": roofline_of(c, "lj13", rs, False)}
+            extra["fm_train"] = bench_train(c, cpu=not args.no_cpu)
+            launches += extra["fm_train"].pop("launches_per_step") * 10
+        cpu = None
+        if c.rank == 0 and c.world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_sample_logq("lj13", host_params("lj13"), CPU_TRAJ, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{CPU_TRAJ} LJ13 trajectories x 121 evals (fixed dt=0.05) in {dt:.1f} s, torch-CPU fp32 restatement of "
+                             "the reference (reverse-mode Jacobian); JAX reference not installable here"}
+            if not args.no_extra:
+                v2, dt2 = cpu_sample_logq("aldp", host_params("aldp"), 2, threads)
+                extra["aldp"]["cpu_baseline"] = {"value": v2, "unit": UNIT, "cores": threads, "kind": "port",
+                                                 "sample": f"2 ALDP trajectories x 121 evals in {dt2:.1f} s"}
+                v3, dt3 = cpu_sample_logq("dw4", host_params("dw4"), 16, threads)
+                extra["dw4"]["cpu_baseline"] = {"value": v3, "unit": UNIT, "cores": threads, "kind": "port",
+                                                "sample": f"16 DW4 trajectories x 121 evals in {dt3:.1f} s"}
+                v4, dt4 = cpu_sample_logq("lj13", host_params("lj13"), 64, threads, div=False)
+                extra["sample_only"]["cpu_baseline"] = {"value": v4, "unit": UNIT, "cores": threads, "kind": "port",
+                                                        "sample": f"64 LJ13 sample_cnf trajectories x 121 evals in {dt4:.1f} s"}
+        line = contract_line(c, args, metric=METRIC, unit=UNIT, r=r,
+                             workload=f"lj13_sample_and_log_prob_exact_dopri5_{fixed_tag}+lj_log_weights+ess",
+                             cfg_extra={"batch_per_gpu": r["batch_this_rank"], "global_batch": r["global_batch"],
+                                        "n_evals_per_sample": r["evals_per_launch"] / r["batch_this_rank"], "parallelism": par},
+                             roofline=roofline_of(c, "lj13", r, True), cpu=cpu, extra=extra,
+                             scaling=args.scaling, launches=launches)
+
+    elif args.workload in ("aldp", "dw4"):
+        name = args.workload
+        b0, b1 = rng_for(12_500 if name == "aldp" else 1024, 100_000 if name == "aldp" else 1024)
+        target = L.TARGET_LJ if name == "aldp" else L.TARGET_DW
+        r = bench_solve(c, name, b0, b1, div=True, adaptive=args.adaptive, steps=args.steps, warmup=args.warmup, target=target,
+                        e2e_steps=1, sample_clocks=True)
+        cpu = None
+        if c.rank == 0 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            nt = 4 if name == "aldp" else 16
+            v, dt = cpu_sample_logq(name, host_params(name), nt, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{nt} {name.upper()} trajectories x 121 evals (fixed dt=0.05) in {dt:.1f} s, torch-CPU fp32 restatement"}
+        metric = (f"{name.upper()} samples/s with exact log-q (Dopri5) + log-weights + ESS"
+                  + (" [log p = LJ-style stand-in on 22 atoms: the reference has no ALDP energy]" if name == "aldp" else ""))
+        line = contract_line(c, args, metric=metric, unit=UNIT, r=r,
+                             workload=f"{name}_sample_and_log_prob_exact_dopri5_{fixed_tag}+log_weights+ess",
+                             cfg_extra={"batch_this_rank": r["batch_this_rank"], "global_batch": r["global_batch"],
+                                        "n_evals_per_sample": r["evals_per_launch"] / r["batch_this_rank"], "parallelism": par},
+                             roofline=roofline_of(c, name, r, True), cpu=cpu,
+                             extra={"reverse_ess": r.get("reverse_ess"), "forward_ess": r.get("forward_ess"), "step_ms": r["step_ms"],
+                                    "kernels_per_step": r.get("kernels_per_step"), "status_failures": r["status_failures"]},
+                             scaling=args.scaling, launches=r["launches_per_step"] * args.steps)
+
+    elif args.workload == "sweep":
+        table = []
+        for gb in (1_000, 10_000, 100_000, 1_000_000):
+            if gb > args.sweep_max:
+                continue
+            b0, b1 = shard(c, gb)
+            r = bench_solve(c, "lj13", b0, b1, div=False, adaptive=args.adaptive, steps=1 if gb >= 100_000 else args.steps,
+                            warmup=1, target=None, e2e_steps=1, count=(gb == 1_000))
+            table.append({"global_batch": gb, "samples_per_s": r["value"], "ms": r["ms_per_step"], "e2e_samples_per_s": r["e2e"]["value"],
+                          "roofline_frac": roofline_of(c, "lj13", r, False)["frac"]})
+            last = r
+        cpu = None
+        if c.rank == 0 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_sample_logq("lj13", host_params("lj13"), 128, threads, div=False)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"128 LJ13 sample_cnf trajectories x 121 evals in {dt:.1f} s (the B = 1k point extrapolates linearly)"}
+        line = contract_line(c, args, metric=f"LJ13 sample_cnf samples/s (no divergence, Dopri5 {fixed_tag}), largest batch of the sweep",
+                             unit=UNIT, r=last, workload="lj13_sample_cnf_sweep (load_checkpoint_measure_sampling_time.py:101-119)",
+                             cfg_extra={"global_batch": last["global_batch"], "parallelism": par},
+                             roofline=roofline_of(c, "lj13", last, False), cpu=cpu, extra={"sweep": table}, scaling="strong",
+                             launches=last["launches_per_step"])
+
+    elif args.workload == "fm":
+        ft = bench_train(c, steps=max(args.steps, 10), cpu=not args.no_cpu)
+        line = {"metric": ft["metric"], "value": ft["value"], "unit": "steps/s", "n_gpus": c.world,
+                "steps": max(args.steps, 10), "warmup": 3, "ms_per_step": ft["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "qm9pos_flow_matching_update_fn_batch512_per_gpu", "global_batch": ft["global_batch"],
+                           "parallelism": f"dp{c.world} (minibatch shards, one NCCL all-reduce of the flat gradient)"},
+                "roofline": ft["roofline"], "cpu_baseline": ft.get("cpu_baseline"), "e2e": ft["e2e"],
+                "gpu_launches": ft["launches_per_step"] * max(args.steps, 10), "extra": {"loss": ft["loss"], "kernels_per_step": ft["kernels_per_step"]}}
+
+    if c.rank == 0:
+        def clean(o):
+            if isinstance(o, dict):
+                return {k: clean(v) for k, v in o.items() if k != "eng"}
+            if isinstance(o, list):
+                return [clean(v) for v in o]
+            return o
+        print(json.dumps(clean(line)))
+    if c.world > 1:
+        c.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

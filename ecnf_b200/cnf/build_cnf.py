@@ -50,6 +50,8 @@ def build_cnf(n_frames: int, dim: int, sigma_min: float, base_scale: float, n_bl
         return eng.base_log_prob(x)
 
     def sample_and_log_prob_base(seed, sample_shape=()):
+        if isinstance(sample_shape, (int, np.integer)):      # distrax accepts an int for a 1-d sample shape
+            sample_shape = (int(sample_shape),)
         n = int(np.prod(sample_shape)) if len(tuple(sample_shape)) else 1
         x = _base(seed, n)
         lp = eng.base_log_prob(x)

@@ -8,7 +8,9 @@ Differences, all documented in DESIGN.md:
     keys) reproduces the reference's threefry draws on the host (utils/jax_random.py); an integer seed uses the library's
     Philox stream keyed by (seed, global sample index) on the device (the fast path);
   * the fixed-step branch of sample_and_log_prob_cnf integrates (x0, 0) -- the reference passes y0=x0 there and
-    cannot run (sample_and_log_prob.py:140).
+    cannot run (sample_and_log_prob.py:140);
+  * diffrax raises when max_steps (4096) is reached; the kernel flags the trajectory in its stats row, and the wrappers
+    raise EcnfError from that flag by default (`check_status=False` skips the device->host read on hot paths).
 """
 from typing import Optional, Tuple
 
@@ -52,7 +54,7 @@ def _jax_base_and_eps(eng, key, B: int, want_eps: bool):
 
 def sample_cnf(cnf: FlowMatchingCNF, params, key, features=None, use_fixed_step_size: bool = False,
                rtol: float = 1e-5, atol: float = 1e-5, step_size: float = 0.05, *, n_samples: Optional[int] = None,
-               x0=None, global_offset: int = 0, return_stats: bool = False):
+               x0=None, global_offset: int = 0, return_stats: bool = False, check_status: bool = True):
     """ecnf/cnf/sample_and_log_prob.py:11-38."""
     eng = cnf.engine
     if x0 is not None:
@@ -69,13 +71,16 @@ def sample_cnf(cnf: FlowMatchingCNF, params, key, features=None, use_fixed_step_
             x0 = eng.base_sample(key, B, global_offset)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
     x1, _, stats = eng.solve(params, L.MODE_SAMPLE, x0, features, ctrl)
+    if check_status:
+        eng.check_status(stats, "sample_cnf")
     out = x1[0] if single else x1
     return (out, stats) if return_stats else out
 
 
 def get_log_prob(cnf: FlowMatchingCNF, params, x, key=None, features=None, approx: bool = False,
                  use_fixed_step_size: bool = False, rtol: float = 1e-5, atol: float = 1e-5, step_size: float = 0.05,
-                 *, eps=None, global_offset: int = 0, return_stats: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                 *, eps=None, global_offset: int = 0, return_stats: bool = False,
+                 check_status: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """ecnf/cnf/sample_and_log_prob.py:41-94: returns (log_p, log_prob_base, delta).  approx=True = the Hutchinson
     branch (:69-78): one probe eps ~ N(0, I) per trajectory, drawn once from `key` (:55) -- or injected with `eps=`."""
     eng = cnf.engine
@@ -84,11 +89,16 @@ def get_log_prob(cnf: FlowMatchingCNF, params, x, key=None, features=None, appro
     x = x.reshape(-1, eng.cfg.D)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
     if approx and eps is None:
+        if key is None:
+            raise L.EcnfError("get_log_prob(approx=True) draws its Hutchinson probe from `key` "
+                              "(sample_and_log_prob.py:55): pass key= (jax-style uint32[2] or an integer seed) or eps=")
         if jr.is_key(key):
             eps = torch.from_numpy(jr.normal_per_key(_jax_keys(key, x.shape[0]), eng.cfg.D)).to(eng.device)
         else:
             eps = eng.normal_noise(key, x.shape[0], global_offset, substream=1)
     _, logs, stats = eng.solve(params, L.MODE_LOGPROB, x, features, ctrl, eps=eps if approx else None)
+    if check_status:
+        eng.check_status(stats, "get_log_prob")
     out = (logs[0, 0], logs[0, 1], logs[0, 2]) if single else (logs[:, 0], logs[:, 1], logs[:, 2])
     return (*out, stats) if return_stats else out
 
@@ -96,7 +106,7 @@ def get_log_prob(cnf: FlowMatchingCNF, params, x, key=None, features=None, appro
 def sample_and_log_prob_cnf(cnf: FlowMatchingCNF, params, key, features=None, approx: bool = False,
                             use_fixed_step_size: bool = False, rtol: float = 1e-5, atol: float = 1e-5,
                             step_size: float = 0.05, *, n_samples: Optional[int] = None, x0=None, eps=None,
-                            global_offset: int = 0, return_stats: bool = False):
+                            global_offset: int = 0, return_stats: bool = False, check_status: bool = True):
     """ecnf/cnf/sample_and_log_prob.py:97-149: returns (x1, log_q).  approx=True = the Hutchinson branch (:123-133); the
     reference draws its probe from the SAME key as the base sample (:130,137; SURVEY C#6), which here means the raw noise
     underneath `sample_base(key)` (substream 0) -- or inject it with `eps=`."""
@@ -116,7 +126,15 @@ def sample_and_log_prob_cnf(cnf: FlowMatchingCNF, params, key, features=None, ap
             x0 = eng.base_sample(key, B, global_offset)
     ctrl = L.make_ctrl(use_fixed_step_size, rtol, atol, step_size)
     if approx and eps is None:
-        eps = eng.normal_noise(key, x0.shape[0], global_offset, substream=0)
+        # x0 was injected: the probe still comes from `key`, as the reference draws it (sample_and_log_prob.py:130)
+        if key is None:
+            raise L.EcnfError("sample_and_log_prob_cnf(approx=True) with x0= given needs key= or eps= for the probe")
+        if jr.is_key(key):
+            eps = torch.from_numpy(jr.normal_per_key(_jax_keys(key, x0.shape[0]), eng.cfg.D)).to(eng.device)
+        else:
+            eps = eng.normal_noise(key, x0.shape[0], global_offset, substream=0)
     x1, logs, stats = eng.solve(params, L.MODE_SAMPLE_LOGQ, x0, features, ctrl, eps=eps if approx else None)
+    if check_status:
+        eng.check_status(stats, "sample_and_log_prob_cnf")
     out = (x1[0], logs[0, 0]) if single else (x1, logs[:, 0])
     return (*out, stats) if return_stats else out

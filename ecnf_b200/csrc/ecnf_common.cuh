@@ -48,11 +48,11 @@ struct ecnf_model {
   const float* d_params;
   int num_sms;
   int device;
+  int engine;   // ecnf_model_set_engine: 0 = tensor cores where eligible, 1 = fp32 SIMT everywhere
 };
 
 EcnfModelDev ecnf_make_dev(const ecnf_model* m, const float* d_params);
 void ecnf_set_error(const char* fmt, ...);
-int ecnf_engine_choice();   // ecnf_set_engine: 0 = tensor cores where eligible, 1 = fp32 SIMT everywhere
 
 #define ECNF_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \

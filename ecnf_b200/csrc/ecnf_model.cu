@@ -127,6 +127,7 @@ int ecnf_model_create(const ecnf_config* cfg, const float* d_params, ecnf_model*
     dev = -1;
   }
   m->device = dev;
+  m->engine = 0;
   *out = m;
   return ECNF_OK;
 }

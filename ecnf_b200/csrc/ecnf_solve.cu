@@ -23,10 +23,8 @@ int grid_for(const ecnf_model* m, int64_t B) {
   return (int)g;
 }
 
-int g_engine = 0;   // 0 = auto (tensor cores where eligible), 1 = force the fp32 SIMT engine
-
-bool use_tc(const ecnf_model* m, bool div) {
-  return g_engine == 0 && tc_eligible(m, div);
+bool use_tc(const ecnf_model* m, bool div) {   // m->engine: 0 = auto (tensor cores where eligible), 1 = fp32 SIMT
+  return m->engine == 0 && tc_eligible(m, div);
 }
 
 int64_t scratch_stride_of(const ecnf_model* m, bool div) {
@@ -61,7 +59,8 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
   a.feat = feat;
   a.eps = div ? eps : nullptr;
   if (ctrl) a.ctrl = *ctrl;
-  else a.ctrl = ecnf_solve_ctrl{0, 0.05f, 1e-5f, 1e-5f, 1e-5f, 4096, 0.9f, 0.2f, 10.f, 5.f};
+  else a.ctrl = ecnf_solve_ctrl{0, 0.05f, 1e-5f, 1e-5f, 1e-5f, 4096, 0.9f, 0.2f, 10.f, 5.f, 1.f};
+  if (!(a.ctrl.err_scale > 0.f)) a.ctrl.err_scale = 1.f;
   a.out_x = out_x;
   a.out_logs = out_logs;
   a.out_stats = out_stats;
@@ -78,8 +77,6 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
 }
 
 }  // namespace
-
-int ecnf_engine_choice() { return g_engine; }
 
 extern "C" {
 
@@ -100,9 +97,9 @@ int ecnf_solve_tc_tile_table(const ecnf_model* m, int kind, uint32_t* out_host, 
   return tc_tile_table(m, kind, out_host, cap_words);
 }
 
-int ecnf_set_engine(int engine) {
-  if (engine != 0 && engine != 1) { ecnf_set_error("ecnf_set_engine: 0 = auto, 1 = fp32 SIMT"); return ECNF_ERR_INVALID; }
-  g_engine = engine;
+int ecnf_model_set_engine(ecnf_model* m, int engine) {
+  if (!m || (engine != 0 && engine != 1)) { ecnf_set_error("ecnf_model_set_engine: 0 = auto, 1 = fp32 SIMT"); return ECNF_ERR_INVALID; }
+  m->engine = engine;
   return ECNF_OK;
 }
 

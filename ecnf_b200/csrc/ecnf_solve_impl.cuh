@@ -752,7 +752,7 @@ __device__ __forceinline__ void solve_body(const KernelArgs& a, Eng& eng, long l
                 const float bj = c_BERR[j];
                 if (bj != 0.f) e = e + bj * kk[j * S + i];
               }
-              red[i] = e / (c.atol + fmaxf(fabsf(y[i]), fabsf(ys[i])) * c.rtol);
+              red[i] = (c.err_scale * e) / (c.atol + fmaxf(fabsf(y[i]), fabsf(ys[i])) * c.rtol);
             }
             const float err = rms_of_red();
             keep = (err < 1.f) || at_dtmin;

@@ -93,7 +93,6 @@ int tc_tile_table(const ecnf_model* mdl, int kind, uint32_t* out, int64_t cap_wo
 }
 
 int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, bool div, cudaStream_t st) {
-  static TcPrepList list;   // filled per call below (host-side scratch; the call is not re-entrant across threads)
   TcPrepList local{};
   a.img.base = reinterpret_cast<const unsigned char*>(image_ws);
   walk_images(mdl, &a.img, &local);
@@ -101,7 +100,6 @@ int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, bo
     ecnf_set_error("tensor-core path: %d weight images exceed the prep list", local.count);
     return ECNF_ERR_UNSUPPORTED;
   }
-  (void)list;
   dim3 pgrid(16, local.count);
   tc_prep_kernel<<<pgrid, 256, 0, st>>>(mdl->d_params, reinterpret_cast<unsigned char*>(image_ws), local);
   ECNF_CHECK_CUDA(cudaGetLastError());

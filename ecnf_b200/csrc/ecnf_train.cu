@@ -19,6 +19,10 @@ using ecnf_tile::NTHREADS;
 using ecnf_tile::tile_gemm;
 using ecnf_tile::WCHUNK;
 
+// engine choice of the model handle of the ecnf_fm_loss_grad call running on this host thread (0 = tensor cores where
+// eligible, 1 = fp32 SIMT): read once at entry, so concurrent callers with different handles do not interfere
+thread_local int t_engine = 0;
+
 __device__ __forceinline__ float silu_f(float z) { return z * ecnf_sigmoid(z); }
 __device__ __forceinline__ float dsilu_f(float z) {
   const float s = ecnf_sigmoid(z);
@@ -123,7 +127,7 @@ template <int K, int N, int K2>
 int launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t st) {
   // the big square edge-row GEMMs go to the tensor cores (ecnf_train_tc.cuh) unless the SIMT engine is forced
   if constexpr (K == N && (K == 128 || K == 256)) {
-    if (!g.A2 && g.M >= 8192 && ecnf_engine_choice() == 0) {
+    if (!g.A2 && g.M >= 8192 && t_engine == 0) {
       ecnf_train_tc::Args a{g.A, g.W, g.bias, g.rowvec, g.rows_per_vec, g.resid, g.add, g.mulz, g.C, g.M, g.a_op};
       ECNF_CHECK_CUDA((ecnf_train_tc::launch<K, N>(a, num_sms, st)));
       return ECNF_OK;
@@ -233,7 +237,7 @@ __global__ void colsum_kernel(const float* __restrict__ Z, int M, int N, float* 
 int launch_dw(const float* A, int lda, int a_op, const float* dZ, int ldz, float* dW, int K, int N, int M, int num_sms,
               cudaStream_t st, float* bias_grad = nullptr) {
   // the big square weight gradients (reduction over the edge rows) go to the tensor cores (ecnf_train_tc.cuh)
-  if (lda == K && ldz == N && K == N && (K == 128 || K == 256) && M >= 8192 && ecnf_engine_choice() == 0) {
+  if (lda == K && ldz == N && K == N && (K == 128 || K == 256) && M >= 8192 && t_engine == 0) {
     if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
     else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
     return ECNF_OK;
@@ -1028,6 +1032,7 @@ int ecnf_fm_loss_grad(const ecnf_model* m, const float* x_data, const float* x0,
     return ECNF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  t_engine = m->engine;
   const int U = m->cfg.mlp_units, H = m->cfg.n_hidden;
   if (U == 128 && H == 64) return fm_run<128, 64>(m, x_data, x0, t, feat, B, loss_denominator, out_loss, out_grad, ws, st);
   if (U == 256 && H == 32) return fm_run<256, 32>(m, x_data, x0, t, feat, B, loss_denominator, out_loss, out_grad, ws, st);

@@ -116,7 +116,7 @@ class Engine:
                 shape = (rows.value, cols.value)
             self.layout.append((path, off.value, shape))
         self._device = device
-        self._ws: Dict[str, torch.Tensor] = {}
+        self._ws: Dict[Tuple[str, int], torch.Tensor] = {}
         self._pack_cache: Dict[int, Tuple[object, PackedParams]] = {}
         self._bound: Optional[torch.Tensor] = None
 
@@ -185,11 +185,29 @@ class Engine:
             self._bound = packed.flat
 
     def _workspace(self, tag: str, nbytes: int) -> torch.Tensor:
-        ws = self._ws.get(tag)
+        """Scratch for one library call, keyed by (kind, current stream): calls issued on different streams never
+        share a buffer (calls on one stream are ordered, so they may)."""
+        key = (tag, torch.cuda.current_stream().cuda_stream)
+        ws = self._ws.get(key)
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
-            self._ws[tag] = ws
+            self._ws[key] = ws
         return ws
+
+    def set_engine(self, engine: int) -> None:
+        """0 = tensor cores where the shape is eligible (default), 1 = fp32 SIMT everywhere.  Per model handle."""
+        L.check(self.lib.ecnf_model_set_engine(self.handle, int(engine)), "ecnf_model_set_engine")
+
+    @staticmethod
+    def check_status(stats: torch.Tensor, what: str) -> None:
+        """diffrax raises when max_steps is reached (throw=True); the kernel flags the trajectory instead.  This is the
+        raise: one device->host read of the status column."""
+        bad = torch.nonzero(stats[:, 3] != 0).flatten()
+        if bad.numel():
+            head = ", ".join(str(int(i)) for i in bad[:8].tolist())
+            raise L.EcnfError(f"{what}: {bad.numel()} of {stats.shape[0]} trajectories reached max_steps before the end "
+                              f"time (first: {head}); their outputs are partial.  Pass check_status=False to get the "
+                              "raw results and inspect return_stats=True yourself.")
 
     def _prep(self, x, feat, B_hint=None):
         dev = self.device

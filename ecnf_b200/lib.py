@@ -34,14 +34,16 @@ class SolveCtrl(C.Structure):
     _fields_ = [
         ("fixed", C.c_int32), ("step_size", C.c_float), ("rtol", C.c_float), ("atol", C.c_float),
         ("dtmin", C.c_float), ("max_steps", C.c_int32), ("safety", C.c_float), ("factormin", C.c_float),
-        ("factormax", C.c_float), ("error_order", C.c_float),
+        ("factormax", C.c_float), ("error_order", C.c_float), ("err_scale", C.c_float),
     ]
 
 
 def make_ctrl(use_fixed_step_size=False, rtol=1e-5, atol=1e-5, step_size=0.05, dtmin=1e-5, max_steps=4096,
-              safety=0.9, factormin=0.2, factormax=10.0, error_order=5.0) -> SolveCtrl:
+              safety=0.9, factormin=0.2, factormax=10.0, error_order=5.0, err_scale=1.0) -> SolveCtrl:
+    """err_scale multiplies the embedded Dopri5 error estimate (1 = diffrax's b_hat weights, 1.5 = the classic
+    Hairer-Wanner ones) -- the same knob as oracle.SolveControl.err_scale."""
     return SolveCtrl(int(bool(use_fixed_step_size)), step_size, rtol, atol, dtmin, max_steps, safety, factormin,
-                     factormax, error_order)
+                     factormax, error_order, err_scale)
 
 
 # every exported symbol of include/ecnf_b200.h with (restype, argtypes)
@@ -57,7 +59,7 @@ SIGNATURES = {
     "ecnf_model_param_layout": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(_I64), C.POINTER(_I64),
                                           C.POINTER(_I64)]),
     "ecnf_solve_workspace_bytes": (_I64, [_P, C.c_int, _I64]),
-    "ecnf_set_engine": (C.c_int, [C.c_int]),
+    "ecnf_model_set_engine": (C.c_int, [_P, C.c_int]),
     "ecnf_solve_tensor_flops_per_eval": (C.c_int64, [C.c_void_p]),
     "ecnf_solve_tc_tile_table": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_int64]),
     "ecnf_vf_forward": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I64, _P]),

@@ -14,13 +14,15 @@ import torch
 from ..engine import CnfConfig, Engine, key_to_seed
 
 
-def init_flat_params(eng: Engine, seed: int, head_variance: float = 0.001) -> np.ndarray:
-    """Reference init statistics: Dense = lecun_normal (flax default), bias 0, Embed N(0, 1/H) (flax default
-    variance_scaling(1, fan_in, normal, out_axis=0)), phi_x head variance_scaling(0.001, fan_avg, uniform)
-    (egnn.py:84), final_scaling 1 (egnn.py:188).  Returns the flat buffer in the engine layout."""
+def init_param_tensors(layout, seed: int, head_variance: float = 0.001) -> dict:
+    """{flax path: fp32 array} for an ordered [(path, shape)] layout (SURVEY Appendix D order).  Reference init
+    statistics: Dense = lecun_normal (flax default), bias 0, Embed N(0, 1/H) (flax default variance_scaling(1, fan_in,
+    normal, out_axis=0)), phi_x head variance_scaling(0.001, fan_avg, uniform) (egnn.py:84), final_scaling 1
+    (egnn.py:188).  Pure numpy: usable without the CUDA library (bench.py's CPU arm draws the same parameters)."""
     rng = np.random.default_rng(seed)
-    flat = np.zeros(eng.param_count, np.float32)
-    for path, off, shape in eng.layout:
+    out = {}
+    for path, shape in layout:
+        shape = tuple(shape)
         leaf = path.split("/")[-1]
         cnt = int(np.prod(shape)) if shape else 1
         if leaf == "final_scaling":
@@ -41,7 +43,17 @@ def init_flat_params(eng: Engine, seed: int, head_variance: float = 0.001) -> np
                 v[bad] = rng.standard_normal(int(bad.sum()))
                 bad = np.abs(v) > 2
             v = v * std
-        flat[off:off + cnt] = v.astype(np.float32)
+        out[path] = v.astype(np.float32).reshape(shape)
+    return out
+
+
+def init_flat_params(eng: Engine, seed: int, head_variance: float = 0.001) -> np.ndarray:
+    """init_param_tensors laid out as the flat buffer of the engine (the library's aligned parameter layout)."""
+    tensors = init_param_tensors([(p, s) for p, _, s in eng.layout], seed, head_variance)
+    flat = np.zeros(eng.param_count, np.float32)
+    for path, off, shape in eng.layout:
+        cnt = int(np.prod(shape)) if shape else 1
+        flat[off:off + cnt] = tensors[path].ravel()
     return flat
 
 

@@ -71,37 +71,53 @@ _ARRAY_RECONSTRUCTORS = {
     ("jax.interpreters.xla", "reconstruct_device_array"),
     ("jaxlib.xla_extension", "_reconstruct_array"),
 }
-_NUMPY_OK = {"_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer"}
-_BUILTINS_OK = {"dict", "list", "tuple", "set", "frozenset", "int", "float", "complex", "bool", "bytes", "bytearray", "str",
-                "slice", "range", "object"}
+def _numpy_table():
+    """name -> object for the few numpy callables an array pickle needs, resolved from modules that are ALREADY imported
+    here -- the module string of the pickle is only compared, never imported."""
+    tab = {"ndarray": np.ndarray, "dtype": np.dtype}
+    import warnings
+    for modname in ("numpy._core.multiarray", "numpy._core.numeric", "numpy.core.multiarray", "numpy.core.numeric"):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", DeprecationWarning)
+                mod = __import__(modname, fromlist=["_"])
+        except ImportError:
+            continue
+        if all(name in tab for name in ("_reconstruct", "scalar", "_frombuffer")):
+            break
+        for name in ("_reconstruct", "scalar", "_frombuffer"):
+            if hasattr(mod, name) and name not in tab:
+                tab[name] = getattr(mod, name)
+    return tab
+
+
+_NUMPY_MODULES = {"numpy", "numpy.core.multiarray", "numpy._core.multiarray", "numpy.core.numeric", "numpy._core.numeric",
+                  "numpy.core", "numpy._core"}
+_NUMPY_TABLE = _numpy_table()
+# constructors only: nothing here can allocate from an attacker-chosen size under REDUCE (no bytearray / range / bytes)
+_BUILTINS_OK = {"dict": dict, "list": list, "tuple": tuple, "set": set, "frozenset": frozenset, "int": int, "float": float,
+                "complex": complex, "bool": bool, "str": str, "slice": slice, "object": object}
 
 
 class _RestrictedUnpickler(pickle.Unpickler):
     def find_class(self, module: str, name: str):
         if (module, name) in _ARRAY_RECONSTRUCTORS:
             return _reconstruct_array
-        if module.startswith("numpy") and name in _NUMPY_OK:
-            if name in ("ndarray", "dtype"):
-                return getattr(np, name)
-            import importlib
-            for mod in (module, "numpy.core.multiarray", "numpy._core.multiarray", "numpy.core.numeric", "numpy._core.numeric"):
-                try:
-                    return getattr(importlib.import_module(mod), name)
-                except (ImportError, AttributeError):
-                    continue
+        if module in _NUMPY_MODULES and name in _NUMPY_TABLE:
+            return _NUMPY_TABLE[name]
         if module == "builtins" and name in _BUILTINS_OK:
-            return getattr(__import__("builtins"), name)
+            return _BUILTINS_OK[name]
         if module == "collections" and name == "OrderedDict":
             import collections
             return collections.OrderedDict
         if module == "copyreg" and name in ("_reconstructor", "__newobj__"):
             import copyreg
             return getattr(copyreg, name)
-        if module.startswith("flax.") and name == "FrozenDict":
+        if (module == "flax" or module.startswith("flax.")) and name == "FrozenDict":
             return _FrozenDict
-        if module.startswith("ecnf.") and name == "TrainingState":
+        if (module == "ecnf" or module.startswith("ecnf.")) and name == "TrainingState":
             return _TrainingState
-        if module.startswith("optax.") or module.startswith("ecnf."):
+        if module == "optax" or module.startswith("optax.") or module == "ecnf" or module.startswith("ecnf."):
             return type(name, (_TaggedTuple,), {"_tag": f"{module}.{name}"})
         raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a checkpoint (not on the white list)")
 
@@ -136,6 +152,33 @@ def loads_reference_checkpoint(data: bytes) -> ReferenceCheckpoint:
         raise ValueError("TrainingState.params is not a flax {'params': ...} pytree")
     return ReferenceCheckpoint(params=params, opt_state=opt_state, key=None if key is None else np.asarray(key),
                                ema_params=None if _is_none_sentinel(ema) else _to_numpy_tree(ema))
+
+
+def find_adam_state(opt_state):
+    """(count, mu, nu) of the optax.adam state inside a reference `opt_state` (setup_training.py:100-109:
+    `optax.adam(lr)` = chain(scale_by_adam, scale_by_learning_rate) -> (ScaleByAdamState(count, mu, nu), ...)), found by
+    class tag wherever the chain nests it; None when there is none."""
+    if isinstance(opt_state, _TaggedTuple) and opt_state._tag.endswith("ScaleByAdamState") and len(opt_state) == 3:
+        return opt_state[0], opt_state[1], opt_state[2]
+    if isinstance(opt_state, (tuple, list)):
+        for item in opt_state:
+            hit = find_adam_state(item)
+            if hit is not None:
+                return hit
+    return None
+
+
+def adam_state_from_checkpoint(ckpt: ReferenceCheckpoint, engine):
+    """ecnf_b200.utils.optim.AdamState (count, mu, nu as flat device buffers in the engine's parameter layout) from the
+    reference checkpoint's optax state, so that training resumes where the reference stopped.  mu / nu have the same
+    pytree structure as the parameters and go through Engine.pack."""
+    from .optim import AdamState
+    hit = find_adam_state(ckpt.opt_state)
+    if hit is None:
+        raise ValueError("no optax ScaleByAdamState in the checkpoint's opt_state")
+    count, mu, nu = hit
+    return AdamState(int(np.asarray(count)), engine.pack(_to_numpy_tree(mu)).flat.clone(),
+                     engine.pack(_to_numpy_tree(nu)).flat.clone())
 
 
 def load_reference_checkpoint(path) -> ReferenceCheckpoint:

@@ -4,7 +4,8 @@
  * ecnf/cnf/{core,build_cnf,sample_and_log_prob,loss,gradient_step}.py and ecnf/nets/egnn.py.  Each entry
  * point below names the reference function (file:line under the reference root) it replaces.  The signatures
  * are XLA-FFI shaped on purpose: device buffers in, device buffers out, scalar attributes, a stream, no hidden
- * state except the opaque model handle -- so a jax.ffi handler is a thin shim.
+ * state except the opaque model handle (config + parameter pointer + engine choice, read at launch time; one handle
+ * per concurrent caller) -- so a jax.ffi handler is a thin shim.
  *
  * Conventions
  *   - every pointer named d_* / x / t / feat / out_* / ws is a DEVICE pointer owned by the caller;
@@ -70,10 +71,11 @@ int ecnf_model_param_layout(const ecnf_model* m, int idx, char* name, int name_c
 #define ECNF_MODE_LOGPROB 4     /* get_log_prob              (sample_and_log_prob.py:41-94)   */
 
 int64_t ecnf_solve_workspace_bytes(const ecnf_model* m, int mode, int64_t B);
-/* Engine selection for the solve / vector-field entry points: 0 = automatic (tcgen05 tensor-core engine where the
- * shape is eligible: mlp_units 128, n_hidden 64, exact divergence; fp32 SIMT otherwise), 1 = always fp32 SIMT
- * (the accuracy reference).  Process-wide.                                                                  */
-int ecnf_set_engine(int engine);
+/* Engine selection of ONE model handle (solve / vector-field / training entry points): 0 = automatic (tcgen05
+ * tensor-core engine where the shape is eligible, fp32 SIMT otherwise), 1 = always fp32 SIMT (the accuracy
+ * reference).  A handle is the triple (config, parameter pointer, engine); every call reads it at launch time, so
+ * concurrent callers (threads / streams) use one handle each -- there is no process-wide state.             */
+int ecnf_model_set_engine(ecnf_model* m, int engine);
 /* tcgen05 flops the tensor-core engine issues per vector-field evaluation with exact divergence (3 bf16 passes over
  * every 128-lane x N-column tile-layer), 0 when the shape runs on the fp32 SIMT engine.  For roofline reports.   */
 int64_t ecnf_solve_tensor_flops_per_eval(const ecnf_model* m);
@@ -105,6 +107,9 @@ typedef struct ecnf_solve_ctrl {
   float dtmin;        /* 1e-5 */
   int32_t max_steps;  /* diffrax default 4096 */
   float safety, factormin, factormax, error_order; /* PIDController defaults 0.9, 0.2, 10, 5 */
+  float err_scale;    /* multiplies the embedded error estimate sum_i (b - b_hat)_i k_i: 1 = diffrax / torchdiffeq's b_hat
+                         (the default; <= 0 is read as 1), 1.5 = the classic Hairer-Wanner b_hat (a
+                         mismatch with the installed diffrax is a configuration change, not a rebuild)              */
 } ecnf_solve_ctrl;
 
 /* mode SAMPLE:       x_init = x0 ~ base;   out_x = x(1);          out_logs unused (may be NULL)

@@ -366,7 +366,8 @@ def dw_energy(x: np.ndarray, a=0.0, b=-4.0, c=0.9, d0=4.0, tau=1.0) -> np.ndarra
 # --------------------------------------------------------------------------------------------------
 # Dormand-Prince 5(4) tableau.  b_err = b - b_hat with the embedded weights diffrax/torchdiffeq use
 # (1951/21600, 0, 22642/50085, 451/720, -12231/42400, 649/6300, 1/60); the classic Hairer weights give an
-# estimate exactly 1.5x larger.  diffrax is not on disk: this is a recollection, exposed as ERR_SCALE.
+# estimate exactly 1.5x larger.  diffrax is not on disk: this is a recollection, exposed as SolveControl.err_scale
+# (and ecnf_solve_ctrl.err_scale in the C-ABI) so that a mismatch is a configuration change.
 DP_C = (0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
 DP_A = (
     (),
@@ -396,6 +397,7 @@ class SolveControl:
     factormin: float = 0.2
     factormax: float = 10.0
     error_order: float = 5.0
+    err_scale: float = 1.0   # multiplies the embedded error estimate (1.5 = classic Hairer-Wanner b_hat)
 
 
 @dataclass
@@ -477,7 +479,7 @@ def dopri5(func: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], y0: torch
             new_prev, new_next = tnext, tnext + dt
         else:
             sc = ctrl.atol + torch.maximum(y.abs(), y1.abs()) * ctrl.rtol
-            err = _rms(yerr / sc)
+            err = _rms(ctrl.err_scale * yerr / sc)
             keep = (err < 1) | at_dtmin
             inv = torch.where(err == 0, torch.full_like(err, float("inf")), 1.0 / err)
             factor = ctrl.safety * inv ** (1.0 / ctrl.error_order)

@@ -25,3 +25,14 @@ def test_reference_arm_is_silent_on_other_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cpu_arm_builds_its_parameters_without_the_cuda_library():
+    """The reference arm must not load libecnf_b200.so (it did, through Engine)."""
+    code = ("import bench; p = bench.host_params('lj13'); "
+            "maps = open('/proc/self/maps').read(); "
+            "print(len(p), 'libecnf_b200' in maps)")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert r.returncode == 0, r.stderr
+    n, loaded = r.stdout.split()
+    assert int(n) > 50 and loaded == "False"

@@ -139,3 +139,28 @@ def test_refuses_foreign_classes():
         loads_reference_checkpoint(pickle.dumps(Evil()))
     with pytest.raises(pickle.UnpicklingError):
         loads_reference_checkpoint(pickle.dumps(collections.Counter("abc")))
+
+
+def test_module_names_are_compared_never_imported():
+    """A module string that merely starts with 'numpy' / 'optax' must not be imported or trusted."""
+    import pickletools  # noqa: F401  (documentation of the opcodes used below)
+    for mod in ("numpyro.evil", "numpy_foo", "optaxx.mod", "flaxy.core"):
+        payload = b"\x80\x02c" + mod.encode() + b"\n_reconstruct\n."
+        with pytest.raises(pickle.UnpicklingError):
+            loads_reference_checkpoint(payload)
+        assert mod not in sys.modules
+    # memory-exhaustion constructors are not on the white list
+    for name in ("bytearray", "range", "bytes"):
+        with pytest.raises(pickle.UnpicklingError):
+            loads_reference_checkpoint(b"\x80\x02cbuiltins\n" + name.encode() + b"\n.")
+
+
+def test_optax_state_adapter_finds_adam_moments():
+    from ecnf_b200.utils.checkpoint import find_adam_state
+    tree, data = _dump_state(True)
+    ck = loads_reference_checkpoint(data)
+    count, mu, nu = find_adam_state(ck.opt_state)
+    assert int(count) == 7
+    _assert_tree_equal(tree, mu)
+    _assert_tree_equal(tree, nu)
+    assert find_adam_state(("nothing", 3)) is None

@@ -133,14 +133,14 @@ def test_tensor_core_engine_is_deterministic_and_agrees_with_simt(case, cuda_dev
     ocfg, flat, tree, eng, x0, feat = _setup(case, B, seed=21)
     ctrl = L.make_ctrl(use_fixed_step_size=True, step_size=0.25)
     try:
-        eng.lib.ecnf_set_engine(0)
+        eng.set_engine(0)
         a = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, ctrl)
         b = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, ctrl)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-        eng.lib.ecnf_set_engine(1)
+        eng.set_engine(1)
         c = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0.numpy(), feat, ctrl)
     finally:
-        eng.lib.ecnf_set_engine(0)
+        eng.set_engine(0)
     assert rel_err(a[0].cpu().numpy(), c[0].cpu().numpy()) < TOL
     la, lc = a[1].cpu().numpy()[:, 0], c[1].cpu().numpy()[:, 0]
     assert np.abs(la - lc).max() < TOL * (np.abs(lc).max() + 1)
@@ -155,14 +155,14 @@ def test_tensor_core_sample_only_agrees_with_simt_and_oracle(case, cuda_device):
     ocfg, flat, tree, eng, x0, feat = _setup(case, B, seed=33)
     ctrl = L.make_ctrl(use_fixed_step_size=True)
     try:
-        eng.lib.ecnf_set_engine(0)
+        eng.set_engine(0)
         a = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, ctrl)
         b = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, ctrl)
         assert torch.equal(a[0], b[0])
-        eng.lib.ecnf_set_engine(1)
+        eng.set_engine(1)
         c = eng.solve(tree, L.MODE_SAMPLE, x0.numpy(), feat, ctrl)
     finally:
-        eng.lib.ecnf_set_engine(0)
+        eng.set_engine(0)
     assert (a[2].cpu().numpy()[:, 2] == 121).all()
     assert rel_err(a[0].cpu().numpy(), c[0].cpu().numpy()) < TOL
     p32 = O.to_torch(flat, torch.float32)

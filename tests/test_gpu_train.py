@@ -126,14 +126,14 @@ def test_tensor_core_gemms_match_simt_and_autograd(case, B, cuda_device):
     eng = Engine(ecfg)
     x_data, x0, t, feat = _batch(ocfg, B, nfeat, 13)
     try:
-        eng.lib.ecnf_set_engine(0)
+        eng.set_engine(0)
         loss_tc, grad_tc = eng.fm_loss_grad(tree, x_data, x0, t, feat.int())
         loss_tc, grad_tc = float(loss_tc[0]), grad_tc.clone()
-        eng.lib.ecnf_set_engine(1)
+        eng.set_engine(1)
         loss_s, grad_s = eng.fm_loss_grad(tree, x_data, x0, t, feat.int())
         loss_s, grad_s = float(loss_s[0]), grad_s.clone()
     finally:
-        eng.lib.ecnf_set_engine(0)
+        eng.set_engine(0)
     assert abs(loss_tc - loss_s) < LOSS_TOL * abs(loss_s)
     assert not torch.equal(grad_tc, grad_s)          # the two paths really differ in arithmetic
     gt = eng.unpack(grad_tc, to_numpy=True)["params"]

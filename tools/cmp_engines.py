@@ -18,7 +18,7 @@ for case, B in (("dw4", 8), ("lj13", 4)):
     x0 = O.base_sample_from_noise(ocfg, torch.tensor(eps)).numpy()
     res = {}
     for e in (1, 0):
-        eng.lib.ecnf_set_engine(e)
+        eng.set_engine(e)
         x1, logs, stats = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0, feat, L.make_ctrl())
         res[e] = (x1.cpu().numpy(), logs.cpu().numpy(), stats.cpu().numpy())
         print(case, "engine", e, "steps", res[e][2][:, 0], "acc", res[e][2][:, 1], "evals", res[e][2][:, 2], "status", res[e][2][:, 3])
@@ -28,8 +28,8 @@ for case, B in (("dw4", 8), ("lj13", 4)):
     t = rng.uniform(0, 1, B).astype(np.float32)
     out = {}
     for e in (1, 0):
-        eng.lib.ecnf_set_engine(e)
+        eng.set_engine(e)
         f, d = eng.apply_div(tree, x0, t, feat)
         out[e] = (f.cpu().numpy(), d.cpu().numpy())
     print(case, "vf rel diff", np.abs(out[0][0] - out[1][0]).max() / np.abs(out[1][0]).max(), "div diff", np.abs(out[0][1] - out[1][1]).max(), "div", out[1][1][:3])
-eng.lib.ecnf_set_engine(0)
+eng.set_engine(0)
