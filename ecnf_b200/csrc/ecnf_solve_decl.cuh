@@ -12,7 +12,7 @@ __host__ __device__ inline int64_t scratch_floats(int n, int dim, int H, int U, 
 
 // byte offsets of the bf16 (hi, lo) weight images used by the tensor-core engine (ecnf_solve_tc.cuh)
 struct TcImgBlock {
-  int Wd, We0s, We0r, We[ECNF_MAX_LAYERS], Wx[ECNF_MAX_LAYERS], Wh0m, Wh0h, Wh[ECNF_MAX_LAYERS], WhL;
+  int Wd, We0, We[ECNF_MAX_LAYERS], Wx[ECNF_MAX_LAYERS], Wh0m, Wh0h, Wh[ECNF_MAX_LAYERS], WhL;
 };
 struct TcImages {
   const unsigned char* base;
@@ -21,14 +21,14 @@ struct TcImages {
 
 // shared-memory carve-up of the tensor-core engine (byte offsets), computed on the host
 struct TcSmemLayout {
-  int bop, macc, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, colw, coloffS, coloffR, colsd, colmrow, colijk, pm, grpw, hdr,
-      pdot, wA, wB, cdbuf, egv, eglen, eginv, egs1, egiz, bars, prof, total_bytes;
-  int mrows;   // rows of the message accumulator (a window of whole receivers)
+  int bop, macc, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, colsd, colmrow, coloffR, chw, hdr, pdot, wA, wB, cdbuf,
+      egv, bars, prof, total_bytes;
+  int mrows;   // rows of the message accumulator (one window of receivers x slots)
 };
 
-// tile tables of the tensor-core engine: which (group, slot) row sits in which accumulator column (ecnf_solve_tc.cuh)
+// tile tables of the tensor-core engine: which (group, slot) rows sit in which 8-column chunk (ecnf_solve_tc.cuh)
 enum { TT_NODE1 = 0, TT_NODE, TT_FIRST, TT_MID, TT_LAST, TT_EDGE1, TT_COUNT };   // *1: primal rows only (no divergence)
-constexpr int TC_TILE_WORDS = 240;   // 128 column + 64 group + 16 header + 16 primal-position + 4 mask words (+ pad)
+constexpr int TC_TILE_WORDS = 48;    // 32 chunk words (2 sub-tiles x 16 chunks) + 16 header words
 struct TcTabs {
   const uint32_t* base;
   int off[TT_COUNT];   // first tile of each kind
@@ -58,7 +58,7 @@ struct KernelArgs {
 template <int U, int H, bool DIV>
 int launch_t(const ecnf_model* mdl, KernelArgs& a, int grid, cudaStream_t st);
 
-// tensor-core engine (U = 128, H = 64, exact divergence): eligibility, extra workspace, launch
+// tensor-core engine ((U, H) = (128, 64) and (64, 32)): eligibility, extra workspace, launch
 bool tc_eligible(const ecnf_model* mdl, bool div);
 int64_t tc_image_bytes(const ecnf_model* mdl);
 int64_t tc_flops_per_eval(const ecnf_model* mdl);

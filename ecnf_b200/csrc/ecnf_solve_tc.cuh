@@ -1,30 +1,36 @@
-// Engine A on the 5th-generation tensor cores (tcgen05 + TMEM), for mlp_units = 128, n_invariant_feat_hidden = 64
-// (DW4 / LJ13 shapes) with the exact divergence.
+// Engine A on the 5th-generation tensor cores (tcgen05 + TMEM): (mlp_units, n_invariant_feat_hidden) = (128, 64)
+// (DW4 / LJ13) and (64, 32) (ALDP), with or without the exact divergence.
 //
 // Same algorithm and tangent-row scheme as the fp32 SIMT engine (ecnf_solve_impl.cuh); the formulation is transposed
 // ("feature on lane") so that everything the tangent rule needs is thread-local:
 //
 //     D^T[out feature (TMEM lane), row (TMEM column)] = W^T (A operand, TMEM) x Act^T (B operand, shared memory)
 //
-//   * a row tile is up to 128 rows = 128 accumulator COLUMNS; thread (f, hh) of the 256 epilogue threads owns output
-//     feature f = lane f and the 64 columns [64 hh, +64) -- the natural tcgen05.ld 32x32b ownership;
-//   * rows are (edge or node, slot) with slot 0 the primal value and slot 1+k the tangent in input direction k.  A tile
-//     is two half-blocks of 64 columns made of segments "primal column, then its tangent columns" (a group split over
-//     the two halves repeats its primal column), so the activation rule  a = silu(z + b) / a-dot = silu'(z) z-dot
-//     is a running scalar per thread: no shared-memory exchange and no barrier between the layers of the MLP chain;
+//   * a row tile is 128 accumulator COLUMNS = 16 chunks of 8 columns; a chunk is "one primal row of an edge / node and
+//     up to 7 of its tangent rows" (a group with more tangents takes several chunks, each repeating the primal column),
+//     so the activation rule  a = silu(z + b) / a-dot = silu'(z_primal) z-dot  is the same straight-line code for every
+//     chunk: column 0 of a chunk is a static register and silu' a per-chunk scalar;
+//   * thread (f, hh) of the 256 epilogue threads owns TMEM lane f and the 64 columns [64 hh, +64) -- the natural
+//     tcgen05.ld 32x32b ownership.  With U = 128 lane = feature; with U = 64 two SUB-TILES are stacked on the lanes
+//     (lanes [0, 64) sub-tile 0, [64, 128) sub-tile 1) and the weights are block-diagonal, so all 128 lanes, all epilogue
+//     threads and the same K = 128 pipeline are used for the narrow network too;
 //   * activations: accumulator (TMEM, fp32) -> registers -> rule -> bf16 (hi, lo) split -> B operand in shared memory,
 //     MN-major no-swizzle canonical layout (8 rows of one feature = one 16-byte store, a warp stores 512 contiguous B);
+//   * phi_e layer 0 (the sender / receiver gather) is an MMA too: node phase 1 leaves h_in as pre-split bf16 (hi | lo)
+//     rows in the CTA's scratch (L2), and the B operand [h_in[sender] | h_in[receiver]] (K-major) of a tile is assembled
+//     by 16-byte cp.async copies -- no register staging, no split, no L2 latency on the epilogue threads;
 //   * weights: pre-split bf16 (hi, lo) images, loaded from L2 straight into TENSOR MEMORY (tcgen05.st) by the epilogue
 //     threads, double buffered, so the MMA reads only B from shared memory;
 //   * every Dense layer is 3 x (K/16) tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~2^-17 relative per
 //     product, measured 4e-6 by tools/probe_tc2.cu) -- single-pass bf16/tf32 misses the 1e-4 tolerance on log q;
-//   * two tiles are in flight (two accumulators, two B buffers): while the epilogue threads work on one, the tensor
-//     core multiplies the other.  A dedicated warp issues the MMAs (the issuing thread blocks while the tensor-core
-//     queue is full, which must not hold up an epilogue warp); hand-over is by mbarriers only
-//     (epilogue threads -> "ready[s]" -> issue warp -> tcgen05.commit -> "done[s]" -> epilogue threads);
-//   * the only cross-lane work are the two Dense(1) heads (attention logit, coordinate head): a 62-shuffle transposing
-//     butterfly per warp + one 4-way sum through shared memory;
-//   * tile composition (which (group, slot) sits in which column) is precomputed per (n, dim, kind) into a table.
+//   * warp roles (384 threads): warps 0-7 epilogue (the MLP chain, the two Dense(1) head dot products, the message
+//     aggregation), warps 8-10 "side" warps, a thread per tile column (per-column metadata, the layer-0 gather, the
+//     coordinate update and its tangents), warp 11 issues the MMAs.  Two tiles are in flight (two accumulators, two B
+//     buffers); all hand-over is by mbarriers:  side -built-> MMA -done-> epilogue -ready-> MMA ... epilogue -heads-> side;
+//   * message aggregation: the chunks of one (receiver, slot group) are consecutive, so their gated messages are summed in
+//     registers and added once per run to a shared-memory accumulator (one copy per thread group: fixed order, run-to-run
+//     deterministic);
+//   * tile composition (which (group, slot) sits in which chunk) is precomputed per (n, dim, kind) into a table.
 #pragma once
 #include "ecnf_solve_impl.cuh"
 #include "ecnf_tc.cuh"
@@ -33,24 +39,20 @@ namespace ecnf_solve_detail {
 
 using namespace ecnf_tc;
 
-constexpr int TCU = 128, TCH = 64;
-constexpr int TC_NT = 288;          // 8 epilogue warps (thread (f, hh) owns feature / TMEM lane f and the column half hh) + 1 MMA-issue warp
-constexpr int TC_EPI = 256;
-#ifndef TC_WPREFETCH
-#define TC_WPREFETCH 0
-#endif
+constexpr int TC_NT = 384;          // 8 epilogue warps + 3 side warps + 1 MMA-issue warp (12 warps: 168 registers each)
+constexpr int TC_EPI = 256, TC_SIDE = 96;
 constexpr int TC_BOP = 65536;       // one B-operand buffer: hi image [K = 128][N = 128] + lo image
-constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;
+constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;       // MN-major B (activations written by the epilogue threads)
+constexpr uint32_t TC_LBO_K = 2048, TC_SBO_K = 128;   // K-major B (the gathered layer-0 operand)
 constexpr int TC_WCOL = 256;        // first TMEM column of the weight buffers (accumulators: [0, 128) and [128, 256))
 
-// column word of a tile table
-constexpr uint32_t CW_VALID = 1u << 31, CW_PRIMAL = 1u << 30, CW_DUP = 1u << 29;
-__host__ __device__ __forceinline__ int cw_gid(uint32_t w) { return (int)(w & 1023u); }
-__host__ __device__ __forceinline__ int cw_q(uint32_t w) { return (int)((w >> 10) & 255u); }
-__host__ __device__ __forceinline__ int cw_pc(uint32_t w) { return (int)((w >> 18) & 63u); }
-enum { TH_NC0 = 0, TH_NC1, TH_N, TH_G0, TH_NG, TH_WIN, TH_FLUSH, TH_IFIRST, TH_ILAST, TH_SEGS };
-// kinds with one row per group (TT_NODE1, TT_EDGE1) pack densely: column = local group index (group words only for the
-// first 64 groups of a tile)
+// chunk word of a tile table
+constexpr uint32_t CH_VALID = 1u << 31, CH_GRPEND = 1u << 22, CH_OWNER = 1u << 23, CH_RUNEND = 1u << 24;
+__host__ __device__ __forceinline__ int ch_gid(uint32_t w) { return (int)(w & 1023u); }
+__host__ __device__ __forceinline__ int ch_qb(uint32_t w) { return (int)((w >> 10) & 255u); }    // slot of column 1 (0: dense chunk)
+__host__ __device__ __forceinline__ int ch_cnt(uint32_t w) { return (int)((w >> 18) & 15u); }     // valid columns, 1..8
+// header words (from word 32 of a tile)
+enum { TH_N = 0, TH_FLUSH, TH_WIN_I, TH_WIN_NR, TH_WIN_S, TH_WIN_NS, TH_NCH /* +sub*2+hh */, TH_IFIRST = 10, TH_ILAST, TH_P, TH_MR };
 
 // sigmoid from ex2.approx / rcp.approx (5 instructions, ~1e-7 absolute: well inside the 3-pass GEMM error)
 __device__ __forceinline__ float fast_sigmoid(float z) {
@@ -60,112 +62,157 @@ __device__ __forceinline__ float fast_sigmoid(float z) {
   return r;
 }
 
-__host__ __device__ inline int tc_macc_rows(int n, int dim) {
+__host__ __device__ inline int tc_rows_of_kind(int kind, int n, int dim) {
   const int ND = 1 + n * dim;
-  const int rw = 40 / ND > 1 ? 40 / ND : 1;
-  return (rw < n ? rw : n) * ND;
+  return (kind == TT_NODE1 || kind == TT_EDGE1) ? 1 : kind == TT_NODE ? ND : kind == TT_FIRST ? 1 + 2 * dim : kind == TT_MID ? ND : 1 + dim;
 }
 
-// Packs the groups (nodes or edges) of one table kind into tiles; returns the tile count, writes them when out != null.
-// Tile = 128 column words | 64 group words (slot split + first columns of the group's segments) | 16 header words |
-// (16 unused) | 4 primal masks.  Padding columns between segments are invalid (word 0).
-__host__ __device__ inline int tc_pack(int kind, int n, int dim, uint32_t* out) {
-  const int D = n * dim, ND = 1 + D;
+// Packs the groups (nodes or edges) of one table kind into tiles of 16 * SUB chunks; returns the tile count, writes them
+// when out != null.  Chunk p of a tile sits in sub-tile p % SUB, column half (p / SUB) % 2, chunk position p / (2 SUB)
+// (both halves and both sub-tiles fill evenly).  MR = rows of the message accumulator: tiles of the message-passing kinds
+// never span two windows (a window = some receivers x a slot range whose aggregate fits MR rows).
+__host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR, uint32_t* out) {
+  const int D = n * dim, ND = 1 + D, nb = n - 1;
   const bool edge = kind >= TT_FIRST;
-  const int ngroups = edge ? n * (n - 1) : n;
-  const int r = (kind == TT_NODE1 || kind == TT_EDGE1) ? 1 : kind == TT_NODE ? ND : kind == TT_FIRST ? 1 + 2 * dim : kind == TT_MID ? ND : 1 + dim;
-  // message-accumulator window: tiles of the message-passing kinds never span two windows of receivers
-  const int window = (kind == TT_FIRST || kind == TT_MID) ? (tc_macc_rows(n, dim) / ND) * (n - 1) : 0;
-  // segments start on 8-column chunk boundaries (the activation rule works chunk-wise); all-primal node tiles pack densely
-  const int al = r == 1 ? 1 : 8;
-  int tile = 0, used0 = 0, used1 = 0, half = 0, ng = 0, g0 = 0;
+  const int ngroups = edge ? n * nb : n;
+  const int r = tc_rows_of_kind(kind, n, dim);
+  const bool dense = (r == 1);
+  const int CAP = 16 * SUB;
+  int tile = 0, p = 0;
+  int win_i = 0, win_nr = 0, win_s = 0, win_ns = 0, i_first = 0, i_last = 0;
+  int run_start = 0;     // first chunk (index in the tile) of the current run
   auto tp = [&](int t) { return out + (size_t)t * TC_TILE_WORDS; };
-  auto close = [&](int gnext, int flush) {
-    if (ng == 0) return;
+  auto word_index = [&](int q) { return (q % SUB) * 16 + ((q / SUB) % 2) * 8 + q / (2 * SUB); };
+  auto end_run = [&]() {       // chunks [run_start, p) form a run: mark its end and the last chunk of every thread group
+    if (out && p > run_start) {
+      tp(tile)[word_index(p - 1)] |= CH_RUNEND;
+      for (int q = run_start; q < p; ++q)
+        if (q + 2 * SUB >= p) tp(tile)[word_index(q)] |= CH_GRPEND;
+    }
+    run_start = p;
+  };
+  auto close = [&](int flush) {
+    if (p == 0) return;
+    end_run();
     if (out) {
-      uint32_t* h = tp(tile) + 192;
-      const int n1 = (used1 + 15) & ~15, n0 = (used0 + 15) & ~15;
-      h[TH_NC0] = (uint32_t)used0;
-      h[TH_NC1] = (uint32_t)used1;
-      h[TH_N] = (uint32_t)(used1 > 0 ? 64 + n1 : (n0 > 16 ? n0 : 16));
-      h[TH_G0] = (uint32_t)g0;
-      h[TH_NG] = (uint32_t)ng;
-      const int wstart = window ? (g0 / window) * window : 0;
-      h[TH_WIN] = (uint32_t)(edge ? wstart / (n - 1) : 0);
-      h[TH_FLUSH] = (uint32_t)flush;
-      h[TH_IFIRST] = (uint32_t)(edge ? g0 / (n - 1) : g0);
-      h[TH_ILAST] = (uint32_t)(edge ? (g0 + ng - 1) / (n - 1) : g0 + ng - 1);
-      // primal masks (4 x 32 columns) and, per half, which 8-column chunks start a segment
-      uint32_t* t = tp(tile);
-      uint32_t segs = 0u;
-      for (int c = 0; c < 128; ++c)
-        if (t[c] & CW_PRIMAL) {
-          t[224 + (c >> 5)] |= 1u << (c & 31);
-          if ((c & 7) == 0) segs |= 1u << (c >> 3);
+      uint32_t* h = tp(tile) + 32;
+      int nmax0 = 0, nmax1 = 0;
+      for (int sb = 0; sb < SUB; ++sb)
+        for (int hh = 0; hh < 2; ++hh) {
+          // chunks q = sb + SUB * hh + 2 SUB * pos < p
+          const int first = sb + SUB * hh;
+          const int cntp = p > first ? (p - first + 2 * SUB - 1) / (2 * SUB) : 0;
+          h[TH_NCH + sb * 2 + hh] = (uint32_t)cntp;
+          if (hh == 0 && cntp > nmax0) nmax0 = cntp;
+          if (hh == 1 && cntp > nmax1) nmax1 = cntp;
         }
-      h[TH_SEGS] = segs;
+      int N = nmax1 > 0 ? 64 + 8 * nmax1 : 8 * nmax0;
+      N = (N + 15) & ~15;
+      h[TH_N] = (uint32_t)(N < 16 ? 16 : N);
+      h[TH_FLUSH] = (uint32_t)flush;
+      h[TH_WIN_I] = (uint32_t)win_i; h[TH_WIN_NR] = (uint32_t)win_nr; h[TH_WIN_S] = (uint32_t)win_s; h[TH_WIN_NS] = (uint32_t)win_ns;
+      h[TH_IFIRST] = (uint32_t)i_first; h[TH_ILAST] = (uint32_t)i_last; h[TH_P] = (uint32_t)p; h[TH_MR] = (uint32_t)MR;
     }
     ++tile;
-    used0 = used1 = 0; half = 0; ng = 0; g0 = gnext;
+    p = 0; run_start = 0;
   };
-  // one segment: [repeated primal] + slots q0..q1-1 from column col0 on
-  auto seg = [&](int g, int col0, int q0, int q1, bool dup) {
-    if (!out) return;
-    uint32_t* cw = tp(tile);
-    int c = col0;
-    const uint32_t common = CW_VALID | (uint32_t)g | ((uint32_t)(col0 & 63) << 18);
-    if (dup) cw[c++] = common | CW_PRIMAL | CW_DUP;
-    for (int q = q0; q < q1; ++q) cw[c++] = common | (q == 0 ? CW_PRIMAL : 0u) | ((uint32_t)q << 10);
+  auto put = [&](int gid, int qb, int cnt, bool owner) {
+    if (p == CAP) close(0);
+    if (p == 0 && out)
+      for (int k = 0; k < TC_TILE_WORDS; ++k) tp(tile)[k] = 0;
+    const int i = edge ? gid / nb : gid;
+    if (p == 0) i_first = i;
+    i_last = edge ? (gid + (dense ? cnt - 1 : 0)) / nb : gid + (dense ? cnt - 1 : 0);
+    if (out)
+      tp(tile)[word_index(p)] = CH_VALID | (uint32_t)gid | ((uint32_t)qb << 10) | ((uint32_t)cnt << 18) | (owner ? CH_OWNER : 0u);
+    ++p;
   };
-  for (int g = 0; g < ngroups; ++g) {
-    if (window && g > 0 && g % window == 0) close(g, 1);
-    for (;;) {
-      if (ng == 0 && used0 == 0 && out)
-        for (int k = 0; k < TC_TILE_WORDS; ++k) tp(tile)[k] = 0;
-      if (half == 0) {
-        used0 = (used0 + al - 1) / al * al;
-        const int rem = 64 - used0;
-        if (r <= rem) {
-          seg(g, used0, 0, r, false);
-          if (out && ng < 64) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)used0 << 8);
-          used0 += r;
-          break;
-        }
-        if (rem >= 2 && 1 + r - rem <= 64) {
-          seg(g, used0, 0, rem, false);
-          seg(g, 64, rem, r, true);
-          if (out) tp(tile)[128 + ng] = (uint32_t)rem | ((uint32_t)used0 << 8) | (64u << 16);
-          used0 = 64; used1 = 1 + r - rem; half = 1;
-          break;
-        }
-        half = 1;
-        if (r > 64) { close(g, 0); }
-        continue;
-      }
-      used1 = (used1 + al - 1) / al * al;
-      const int rem = 64 - used1;
-      if (r <= rem) {
-        seg(g, 64 + used1, 0, r, false);
-        if (out && ng < 64) tp(tile)[128 + ng] = (uint32_t)r | ((uint32_t)(64 + used1) << 8);
-        used1 += r;
-        break;
-      }
-      close(g, 0);
+  if (dense) {                       // TT_NODE1 / TT_EDGE1: 8 consecutive groups per chunk, every column a primal row
+    win_i = 0; win_nr = n; win_s = 0; win_ns = 1;
+    for (int g = 0; g < ngroups; g += 8) {
+      put(g, 0, ngroups - g < 8 ? ngroups - g : 8, true);
+      end_run();
     }
-    ++ng;
+    close(kind == TT_EDGE1 ? 1 : 0);
+    return tile;
   }
-  close(ngroups, (window || kind == TT_EDGE1) ? 1 : 0);     // the primal-only edge kind aggregates over one window = all receivers
+  if (kind == TT_NODE) {             // (node, slot group) chunks, no windows
+    for (int g = 0; g < n; ++g)
+      for (int qb = 1; qb < r; qb += 7) { put(g, qb, 1 + (r - qb < 7 ? r - qb : 7), qb == 1); end_run(); }
+    close(0);
+    return tile;
+  }
+  if (kind == TT_LAST) {             // one chunk per edge; a run = the edges of one receiver (coordinate sums)
+    for (int i = 0; i < n; ++i) {
+      for (int e = i * nb; e < (i + 1) * nb; ++e) {
+        if (p == CAP) close(0);
+        put(e, 1, r, true);
+      }
+      end_run();
+    }
+    close(0);
+    return tile;
+  }
+  if (kind == TT_FIRST) {            // one chunk per edge; accumulator rows: (receiver, {primal, its own dim directions})
+    const int rows_per = 1 + dim;
+    int W = MR / rows_per; if (W < 1) W = 1; if (W > n) W = n;
+    for (int i0 = 0; i0 < n; i0 += W) {
+      win_i = i0; win_nr = (n - i0 < W) ? n - i0 : W; win_s = 0; win_ns = rows_per;
+      for (int i = i0; i < i0 + win_nr; ++i)
+        for (int e = i * nb; e < (i + 1) * nb; ++e) {
+          if (p == CAP) close(0);
+          put(e, 1, r, true);
+          end_run();                 // per-sender directions: every chunk is flushed on its own
+        }
+      close(1);
+    }
+    return tile;
+  }
+  // TT_MID: windows of whole receivers when ND <= MR, else one receiver x a slot range made of whole chunks
+  if (ND <= MR) {
+    int W = MR / ND; if (W > n) W = n;
+    for (int i0 = 0; i0 < n; i0 += W) {
+      win_i = i0; win_nr = (n - i0 < W) ? n - i0 : W; win_s = 0; win_ns = ND;
+      for (int i = i0; i < i0 + win_nr; ++i)
+        for (int qb = 1; qb < r; qb += 7) {
+          for (int e = i * nb; e < (i + 1) * nb; ++e) {
+            if (p == CAP) close(0);
+            put(e, qb, 1 + (r - qb < 7 ? r - qb : 7), qb == 1);
+          }
+          end_run();
+        }
+      close(1);
+    }
+  } else {
+    const int cpw = (MR - 1) / 7 > 0 ? (MR - 1) / 7 : 1;       // chunks (slot groups) per window
+    for (int i = 0; i < n; ++i)
+      for (int qw = 1; qw < r; qw += 7 * cpw) {
+        const int q_end = (qw + 7 * cpw < r) ? qw + 7 * cpw : r;
+        win_i = i; win_nr = 1; win_s = (qw == 1) ? 0 : qw; win_ns = q_end - win_s;
+        for (int qb = qw; qb < q_end; qb += 7) {
+          for (int e = i * nb; e < (i + 1) * nb; ++e) {
+            if (p == CAP) close(0);
+            put(e, qb, 1 + (r - qb < 7 ? r - qb : 7), qb == 1);
+          }
+          end_run();
+        }
+        close(1);
+      }
+  }
   return tile;
 }
 
-__host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim) {
+// shared-memory carve-up; MR (rows of the message accumulator) is the largest 1 + 7k (<= ND) that fits in 227 KB
+template <int U, int H>
+__host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim, int MR) {
+  constexpr int SUB = 128 / U;
   const int D = n * dim, S = D + 1, E = n * (n - 1);
   TcSmemLayout L;
   int o = 0;
   auto take = [&](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
   L.bop = take(2 * TC_BOP);
-  L.mrows = tc_macc_rows(n, dim);
-  L.macc = take(2 * (L.mrows + 1) * TCU * 4);   // aggregated messages of the receiver window, one copy per column half (+ a dump row)
+  L.mrows = MR;
+  L.macc = take(2 * SUB * (MR + 1) * U * 4);   // one copy per (column half, sub-tile) thread group, + a dump row each
   L.xt = take(D * D * 4);
   L.xtacc = take(D * D * 4);
   L.dacc = take(D * 4);
@@ -177,28 +224,32 @@ __host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim) {
   L.cvec = take(64 * 4);
   L.ode = take(11 * S * 4);
   L.red = take((S + 16) * 4);
-  L.colw = take(2 * 128 * 4);
-  L.coloffS = take(2 * 128 * 4);
-  L.coloffR = take(2 * 128 * 4);
-  L.colsd = take(2 * 128 * 4);
-  L.colmrow = take(2 * 128 * 4);
-  L.colijk = take(2 * 128 * 4);
-  L.pm = take(2 * 4 * 4);
-  L.grpw = take(2 * 64 * 4);
+  L.colsd = take(2 * SUB * 128 * 4);
+  L.colmrow = take(2 * SUB * 128 * 4);
+  L.coloffR = take(2 * SUB * 128 * 4);
+  L.chw = take(2 * 32 * 4);
   L.hdr = take(2 * 16 * 4);
   L.pdot = take(2 * 8 * 64 * 4);
   L.wA = take(8 * 64 * 4);
   L.wB = take(8 * 64 * 4);
-  L.cdbuf = take(2 * 128 * 3 * 4);
+  L.cdbuf = take(SUB * 128 * 3 * 4);
   L.egv = take(E * 3 * 4);
-  L.eglen = take(E * 4);
-  L.eginv = take(E * 4);
-  L.egs1 = take(E * 4);
-  L.egiz = take(E * 4);
-  L.bars = take(64);
+  L.bars = take(128);
   L.prof = take(32 * 8);
   L.total_bytes = o;
   return L;
+}
+template <int U, int H>
+__host__ inline int tc_pick_mrows(int n, int dim, bool div) {
+  const int ND = div ? 1 + n * dim : 1;
+  if (!div) return n;                                   // primal-only edge tiles aggregate over all receivers at once
+  int best = 0;
+  const int cap = ND > 40 ? ND : 40;                    // whole receivers per window where they are small
+  for (int mr = 8; mr <= cap; ++mr) {
+    if (mr < ND && (mr - 1) % 7 != 0) continue;
+    if (make_tc_layout<U, H>(n, dim, mr).total_bytes + 1024 <= 227 * 1024) best = mr;
+  }
+  return best;
 }
 
 extern __shared__ __align__(1024) unsigned char smem_tc[];
@@ -210,22 +261,25 @@ extern __shared__ __align__(1024) unsigned char smem_tc[];
 #define TCW(field) (reinterpret_cast<uint32_t*>(smem_tc + a.lay.field))
 
 // DIV = false: sample_cnf without a divergence -- primal rows only (tile kinds TT_NODE1 / TT_EDGE1, no tangent state)
-template <bool DIV>
+template <int U_, int H_, bool DIV>
 struct EngineTC {
-  static constexpr int U = TCU, H = TCH;
+  static constexpr int U = U_, H = H_, SUB = 128 / U_;
   static constexpr int NT = TC_NT;
+  static constexpr int KN = SUB * H;      // K of the node-level layers (h rows of both sub-tiles)
+  static constexpr int ROWB = 4 * H;      // bytes of one pre-split h_in row: H bf16 hi | H bf16 lo
   const KernelArgs& a;     // the __grid_constant__ kernel parameter
   const EcnfModelDev& m;
   const TcImages& img;
   const int n, dim, D, ND, E;
-  const int tid, f, hh, warp, lane;
-  const bool is_epi;
+  const int tid, f, hh, warp, lane, sub, fu;
+  const bool is_epi, is_side;
   uint32_t tmem;         // TMEM base address
   uint32_t lane_addr;    // (32 * (warp & 3)) << 16
-  uint32_t ph0, ph1;     // phase counters of the two slots (ready[] for the issue warp, done[] for the epilogue threads)
+  uint32_t par;          // phase parities of the mbarriers this thread waits on: bit (kind * 2 + slot)
 
-  enum { P_NODE_PRE, P_EDGE, P_NODE_POST, P_WAIT, P_BUILD, P_EPI, P_MSG, P_COORD, P_WLOAD, P_META, P_CTRL_WAIT, P_MISC,
-         P_EPI_LD, P_EPI_ACT, P_EPI_ST, P_ARRIVE, P_GATHER, P_NCOUNT };
+  enum { B_READY = 0, B_DONE = 1, B_BUILT = 2, B_HEADS = 3 };
+  enum { P_NODE_PRE, P_EDGE, P_NODE_POST, P_WAIT, P_EPI, P_MSG, P_HEAD, P_WLOAD, P_SIDE_WAIT, P_SIDE_GATHER, P_SIDE_COORD,
+         P_SIDE_META, P_SIDE_CPWAIT, P_NBUILD, P_NCOUNT };
 #ifdef ECNF_TC_PROFILE
   long long prof_t0, prof_t1;
   __device__ __forceinline__ long long* prof_s() const { return reinterpret_cast<long long*>(smem_tc + a.lay.prof); }
@@ -243,25 +297,26 @@ struct EngineTC {
   __device__ __forceinline__ void set_eps(const float*) {}   // Hutchinson probes run on the SIMT engine
   __device__ __forceinline__ float* ode_ptr() const { return TCF(ode); }
   __device__ __forceinline__ float* red_ptr() const { return TCF(red); }
-  __device__ __forceinline__ uint64_t* bar_ready(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + s; }
-  __device__ __forceinline__ uint64_t* bar_done(int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + 2 + s; }
-  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars + 32); }
-  // per-CTA global scratch (L2 resident): h, h_in [n][ND][H]; P_s, P_r, aggregated messages, P_h [n][ND][U]
+  __device__ __forceinline__ uint64_t* bar(int kind, int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + kind * 2 + s; }
+  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(smem_tc + a.lay.bars + 96); }
+  // per-CTA global scratch (L2 resident): h, h_in [n][ND][H] fp32; aggregated messages, P_h [n][ND][U] fp32;
+  // h_in as pre-split bf16 rows [n * ND + 1][hi H | lo H] (the last row is all zero)
   __device__ __forceinline__ float* hA() const { return a.scratch + (size_t)blockIdx.x * a.scratch_stride; }
   __device__ __forceinline__ float* hB() const { return hA() + (size_t)n * ND * H; }
-  __device__ __forceinline__ float* Ps() const { return hB() + (size_t)n * ND * H; }
-  // P_s and P_r carry one extra, all-zero row (index n * ND): the gather of phi_e layer 0 points there for rows without a P part
-  __device__ __forceinline__ float* Pr() const { return Ps() + ((size_t)n * ND + 1) * U; }
-  __device__ __forceinline__ float* Mg() const { return Pr() + ((size_t)n * ND + 1) * U; }
+  __device__ __forceinline__ float* Mg() const { return hB() + (size_t)n * ND * H; }
   __device__ __forceinline__ float* Ph() const { return Mg() + (size_t)n * ND * U; }
+  __device__ __forceinline__ unsigned char* Himg() const { return reinterpret_cast<unsigned char*>(Ph() + (size_t)n * ND * U); }
 
   __device__ __forceinline__ EngineTC(const KernelArgs& a_)
       : a(a_), m(a_.m), img(a_.img), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim), ND(DIV ? 1 + a_.m.n * a_.m.dim : 1),
         E(a_.m.n * (a_.m.n - 1)), tid(threadIdx.x), f(threadIdx.x & 127), hh((threadIdx.x >> 7) & 1), warp(threadIdx.x >> 5),
-        lane(threadIdx.x & 31), is_epi(threadIdx.x < TC_EPI) {
+        lane(threadIdx.x & 31), sub((threadIdx.x & 127) / U_), fu((threadIdx.x & 127) % U_), is_epi(threadIdx.x < TC_EPI),
+        is_side(threadIdx.x >= TC_EPI && threadIdx.x < TC_EPI + TC_SIDE) {
     if (tid == 0) {
-      mbar_init(bar_ready(0), TC_EPI); mbar_init(bar_ready(1), TC_EPI);
-      mbar_init(bar_done(0), 1); mbar_init(bar_done(1), 1);
+      mbar_init(bar(B_READY, 0), TC_EPI); mbar_init(bar(B_READY, 1), TC_EPI);
+      mbar_init(bar(B_DONE, 0), 1); mbar_init(bar(B_DONE, 1), 1);
+      mbar_init(bar(B_BUILT, 0), TC_SIDE); mbar_init(bar(B_BUILT, 1), TC_SIDE);
+      mbar_init(bar(B_HEADS, 0), TC_EPI); mbar_init(bar(B_HEADS, 1), TC_EPI);
 #ifdef ECNF_TC_PROFILE
       for (int k = 0; k < P_NCOUNT; ++k) prof_s()[k] = 0;
 #endif
@@ -273,7 +328,7 @@ struct EngineTC {
     tc_fence_after();
     tmem = *tmem_slot();
     lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    ph0 = ph1 = 0;
+    par = 0;
     if (is_epi) {   // accumulators start finite (columns beyond a tile's N are read but never used)
       uint32_t z[32];
 #pragma unroll
@@ -281,8 +336,9 @@ struct EngineTC {
 #pragma unroll
       for (int q = 0; q < 4; ++q) tmem_st32(tmem + lane_addr + 128u * hh + 32u * q, z);
       tmem_wait_st();
-      (hh ? Pr() : Ps())[(size_t)n * ND * U + f] = 0.f;      // the zero rows of P_s / P_r
     }
+    if (is_side)    // the all-zero row of the pre-split h_in image
+      for (int k = tid - TC_EPI; k < ROWB / 4; k += TC_SIDE) reinterpret_cast<uint32_t*>(Himg() + (size_t)n * ND * ROWB)[k] = 0u;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -297,35 +353,36 @@ struct EngineTC {
     if (warp == 0) tmem_dealloc(tmem, 512);
   }
 
-  // ---- hand-over between the epilogue threads and the MMA-issue warp ----------------------------------------------
+  // ---- hand-over between the thread groups ----------------------------------------------------------------------------
   __device__ __forceinline__ void epi_bar() const { named_bar_sync(1, TC_EPI); }
   // the four warps that own one column half (their partial dot products are summed by each of them)
   __device__ __forceinline__ void half_bar() const { named_bar_sync(2 + hh, TC_EPI / 2); }
-  __device__ __forceinline__ void wait_slot(uint64_t* bar, int s) {
-    const uint32_t par = (s ? ph1 : ph0) & 1u;
-    mbar_wait_parked(bar, par, 20000u);
-    ph0 += (s == 0); ph1 += (s != 0);
+  __device__ __forceinline__ void side_bar() const { named_bar_sync(4, TC_SIDE); }
+  __device__ __forceinline__ void phase_bar() const { named_bar_sync(5, TC_EPI + TC_SIDE); }   // epilogue + side threads
+  __device__ __forceinline__ void wait_bar(int kind, int s) {
+    const uint32_t bit = 1u << (kind * 2 + s);
+    mbar_wait_parked(bar(kind, s), (par & bit) ? 1u : 0u, 20000u);
+    par ^= bit;
     tc_fence_after();
   }
-  __device__ __forceinline__ void wait_done(int s) { qbeg(); wait_slot(bar_done(s), s); qend(P_WAIT); }
-  // epilogue threads: my part of slot s's next operands (B in shared memory, weights / drained accumulator in TMEM) is complete
-  __device__ __forceinline__ void arrive_ready(int s) {
-    qbeg();
+  __device__ __forceinline__ void wait_done(int s) { qbeg(); wait_bar(B_DONE, s); qend(P_WAIT); }
+  // my part of slot s's next operands (B in shared memory, weights / drained accumulator in TMEM) is complete
+  __device__ __forceinline__ void arrive(int kind, int s) {
     fence_proxy_async();
     tc_fence_before();
-    mbar_arrive(bar_ready(s));
-    qend(P_ARRIVE);
+    mbar_arrive(bar(kind, s));
   }
-  // issue warp: wait for all epilogue threads, then acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s]
-  // (K x N), 3-pass split; commit -> done[s]
-  __device__ __forceinline__ void issue_mma(int s, uint32_t a_col, int K) {
+  // issue warp: wait for the producers, then acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s]
+  // (K x N), 3-pass split; commit -> done[s].  kmajor: B is the gathered layer-0 operand.
+  __device__ __forceinline__ void issue_mma(int s, int wait_kind, uint32_t a_col, int K, bool kmajor) {
     if (lane == 0) {
-      wait_slot(bar_ready(s), s);
+      wait_bar(wait_kind, s);
       const int N = hdr(s, TH_N);
-      const uint32_t idesc = make_idesc_bf16(128, N) | IDESC_B_MN;
+      const uint32_t idesc = make_idesc_bf16(128, N) | (kmajor ? 0u : IDESC_B_MN);
       const uint32_t bsm = smem_u32(smem_tc + a.lay.bop) + (uint32_t)s * TC_BOP;
-      uint64_t bh = make_sdesc(bsm, TC_LBO, TC_SBO);
-      uint64_t bl = make_sdesc(bsm + 32768u, TC_LBO, TC_SBO);
+      const uint32_t lbo = kmajor ? TC_LBO_K : TC_LBO, sbo = kmajor ? TC_SBO_K : TC_SBO;
+      uint64_t bh = make_sdesc(bsm, lbo, sbo);
+      uint64_t bl = make_sdesc(bsm + 32768u, lbo, sbo);
       const uint32_t acc = tmem + 128u * s;
       uint32_t a_hi = tmem + a_col, a_lo = tmem + a_col + (uint32_t)(K >> 1);
       const int nk = K >> 4;
@@ -333,16 +390,16 @@ struct EngineTC {
       mma_ts(acc, a_lo, bh, idesc, 1u);
       mma_ts(acc, a_hi, bl, idesc, 1u);
       for (int ks = 1; ks < nk; ++ks) {
-        bh += (2u * TC_LBO) >> 4; bl += (2u * TC_LBO) >> 4; a_hi += 8; a_lo += 8;
+        bh += (2u * lbo) >> 4; bl += (2u * lbo) >> 4; a_hi += 8; a_lo += 8;
         mma_ts(acc, a_hi, bh, idesc, 1u);
         mma_ts(acc, a_lo, bh, idesc, 1u);
         mma_ts(acc, a_hi, bl, idesc, 1u);
       }
-      mma_commit(bar_done(s));
+      mma_commit(bar(B_DONE, s));
     }
   }
 
-  // ---- per-thread column helpers (thread (f, hh): feature f, columns [64 hh, +64) of slot s) -----------------------
+  // ---- per-thread column helpers (thread (f, hh): TMEM lane f, columns [64 hh, +64) of slot s) ------------------------
   __device__ __forceinline__ uint32_t my_acc(int s) const { return tmem + 128u * s + lane_addr + 64u * hh; }
   __device__ __forceinline__ void ld_acc(int s, float (&v)[64]) {
     uint32_t x[32], y[32];
@@ -353,9 +410,9 @@ struct EngineTC {
 #pragma unroll
     for (int c = 0; c < 32; ++c) { v[c] = __uint_as_float(x[c]); v[32 + c] = __uint_as_float(y[c]); }
   }
-  // B operand of slot s <- v (K row = my feature), bf16 hi / lo
-  __device__ __forceinline__ void write_B(int s, const float (&v)[64]) {
-    unsigned char* base = smem_tc + a.lay.bop + s * TC_BOP + (8 * hh) * (int)TC_SBO + f * 16;
+  // B operand of slot s (MN-major) <- v at K row `krow`, bf16 hi / lo
+  __device__ __forceinline__ void write_B(int s, const float (&v)[64], int krow) {
+    unsigned char* base = smem_tc + a.lay.bop + s * TC_BOP + (8 * hh) * (int)TC_SBO + krow * 16;
 #pragma unroll
     for (int g8 = 0; g8 < 8; ++g8) {
       uint32_t h[4], l[4];
@@ -365,41 +422,44 @@ struct EngineTC {
       *reinterpret_cast<uint4*>(base + 32768 + g8 * (int)TC_SBO) = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
-  // Activation rule: a = silu(z + bias) on primal columns, a-dot = silu'(z_primal) z-dot on the tangent columns that
-  // follow them.  Segments start on 8-column chunk boundaries, so the primal column of a segment is column 0 of a chunk
-  // (a static register) and silu' is a running per-thread scalar; `segs` = which of my 8 chunks start a segment.
-  __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int s) {
-    if constexpr (!DIV) {      // every column is a primal row; chunks beyond the used columns of my half are skipped
-      const int nc = hdr(s, TH_NC0 + hh);   // (the sigmoid is MUFU bound and these tiles are mostly padding)
+  __device__ __forceinline__ int hdr(int s, int k) const { return TCI(hdr)[s * 16 + k]; }
+  __device__ __forceinline__ int my_nch(int s) const { return hdr(s, TH_NCH + sub * 2 + hh); }   // chunks in use in my 64 columns
+  __device__ __forceinline__ uint32_t my_chw(int s, int ch) const { return TCW(chw)[s * 32 + sub * 16 + 8 * hh + ch]; }
+  // Activation rule: a = silu(z + bias) on the primal column of every chunk, a-dot = silu'(z_primal) z-dot on the 7 tangent
+  // columns behind it.  L0: z gets the rank-1 |v|^2 term of phi_e layer 0 first (sd = the tile's per-column table, wdf =
+  // my feature's entry of w_d).  Chunks beyond the used ones are zeroed (the MMA reads them).
+  template <bool L0>
+  __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int s, float wdf) {
+    const int nc = my_nch(s);
+    const float* sdp = TCF(colsd) + (s * SUB + sub) * 128 + 64 * hh;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        if (8 * ch < nc) {
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch < nc) {
+        if constexpr (L0) {
+          const float4 s0 = reinterpret_cast<const float4*>(sdp)[2 * ch], s1 = reinterpret_cast<const float4*>(sdp)[2 * ch + 1];
+          v[8 * ch] = fmaf(s0.x, wdf, v[8 * ch]); v[8 * ch + 1] = fmaf(s0.y, wdf, v[8 * ch + 1]);
+          v[8 * ch + 2] = fmaf(s0.z, wdf, v[8 * ch + 2]); v[8 * ch + 3] = fmaf(s0.w, wdf, v[8 * ch + 3]);
+          v[8 * ch + 4] = fmaf(s1.x, wdf, v[8 * ch + 4]); v[8 * ch + 5] = fmaf(s1.y, wdf, v[8 * ch + 5]);
+          v[8 * ch + 6] = fmaf(s1.z, wdf, v[8 * ch + 6]); v[8 * ch + 7] = fmaf(s1.w, wdf, v[8 * ch + 7]);
+        }
+        if constexpr (!DIV) {      // every column is a primal row
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float z = v[8 * ch + u] + bias;
             v[8 * ch + u] = z * fast_sigmoid(z);
           }
         } else {
+          const float z = v[8 * ch] + bias;
+          const float sg = fast_sigmoid(z);
+          const float cur = sg * (1.f + z * (1.f - sg));
+          v[8 * ch] = z * sg;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[8 * ch + u] = 0.f;
+          for (int u = 1; u < 8; ++u) v[8 * ch + u] *= cur;
         }
-      }
-      return;
-    }
-    const uint32_t segs = (TCW(hdr)[s * 16 + TH_SEGS] >> (8 * hh)) & 0xffu;
-    float cur = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      if ((segs >> ch) & 1u) {
-        const float z = v[8 * ch] + bias;
-        const float sg = fast_sigmoid(z);
-        cur = sg * (1.f + z * (1.f - sg));
-        v[8 * ch] = z * sg;
       } else {
-        v[8 * ch] *= cur;
-      }
 #pragma unroll
-      for (int u = 1; u < 8; ++u) v[8 * ch + u] *= cur;
+        for (int u = 0; u < 8; ++u) v[8 * ch + u] = 0.f;
+      }
     }
   }
   template <int W>   // 2W partial sums -> W, exchanging with lane ^ (W/2)
@@ -411,7 +471,7 @@ struct EngineTC {
       x[i] = keep + __shfl_xor_sync(0xffffffffu, send, W >> 1);
     }
   }
-  // column sums over the 32 features of this warp of v[c] * wf (transposing butterfly): lane l ends with the columns
+  // column sums over the 32 lanes of this warp of v[c] * wf (transposing butterfly): lane l ends with the columns
   // 2l and 2l+1 of its half, stored to pd[2l], pd[2l+1]
   __device__ __forceinline__ void warp_dot(const float (&v)[64], float wf, float* pd) {
     float x[32];
@@ -430,10 +490,17 @@ struct EngineTC {
     bfly_round<2>(x);
     *reinterpret_cast<float2*>(pd + 2 * lane) = make_float2(x[0], x[1]);
   }
+  // complete dot product of column c (0..63 of half h2) of sub-tile sb from the per-warp partials of slot s
+  __device__ __forceinline__ float full_dot(int s, int h2, int sb, int c) const {
+    const float* p4 = TCF(pdot) + s * 512 + (4 * h2) * 64 + c;
+    if constexpr (SUB == 1) return (p4[0] + p4[64]) + (p4[128] + p4[192]);
+    else return p4[(2 * sb) * 64] + p4[(2 * sb + 1) * 64];
+  }
   // weight image (hi | lo, K x 128 lanes) -> registers -> TMEM columns [col, col + K)
   template <int K>
-  __device__ __forceinline__ void fetch_w(int img_off, uint32_t (&wv)[2][K / 4]) {
+  __device__ __forceinline__ void load_w(int img_off, uint32_t col) {
     constexpr int NC = K / 16;     // uint4 chunks per thread and part
+    uint32_t wv[2][K / 4];
     const uint4* src = reinterpret_cast<const uint4*>(img.base + img_off);
 #pragma unroll
     for (int p = 0; p < 2; ++p)
@@ -442,9 +509,6 @@ struct EngineTC {
         const uint4 q = __ldg(src + (size_t)(p * (K / 8) + hh * NC + j) * 128 + f);
         wv[p][4 * j] = q.x; wv[p][4 * j + 1] = q.y; wv[p][4 * j + 2] = q.z; wv[p][4 * j + 3] = q.w;
       }
-  }
-  template <int K>
-  __device__ __forceinline__ void store_w(const uint32_t (&wv)[2][K / 4], uint32_t col) {
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       const uint32_t addr = tmem + col + lane_addr + (uint32_t)(p * (K / 2) + hh * (K / 4));
@@ -453,33 +517,28 @@ struct EngineTC {
     }
     tmem_wait_st();
   }
-  template <int K>
-  __device__ __forceinline__ void load_w(int img_off, uint32_t col) {
-    uint32_t wv[2][K / 4];
-    fetch_w<K>(img_off, wv);
-    store_w<K>(wv, col);
-  }
 
   // ---- tile tables ---------------------------------------------------------------------------------------------------
   __device__ __forceinline__ const uint32_t* tile_ptr(int kind, int tile) const {
     return a.tabs.base + (size_t)(a.tabs.off[kind] + tile) * TC_TILE_WORDS;
   }
-  __device__ __forceinline__ int hdr(int s, int k) const { return TCI(hdr)[s * 16 + k]; }
-  // threads 128..227 copy the tile's group words, header, primal-column positions and primal masks
-  __device__ __forceinline__ void meta_copy(int s, const uint32_t* tp) {
-    if (tid >= 128 && tid < 228) {
-      const uint32_t w = __ldg(tp + tid);
-      if (tid < 192) TCW(grpw)[s * 64 + (tid - 128)] = w;
-      else if (tid < 208) TCW(hdr)[s * 16 + (tid - 192)] = w;
-      else if (tid >= 224) TCW(pm)[s * 4 + (tid - 224)] = w;
-    }
+  // (valid, group id, slot q) of column c (0..127) given its chunk word
+  __device__ __forceinline__ bool col_of(uint32_t cw, int c, int& gid, int& q) const {
+    const int u = c & 7;
+    const bool valid = (cw & CH_VALID) && u < ch_cnt(cw);
+    const int qb = ch_qb(cw);
+    if (qb == 0) { gid = ch_gid(cw) + u; q = 0; }       // dense chunk: 8 consecutive groups, primal rows
+    else { gid = ch_gid(cw); q = (u == 0) ? 0 : qb + u - 1; }
+    return valid;
   }
 
   // =============================================================================================================
   // The software pipeline shared by the three phases.  P provides
-  //   ntiles, NL (layers per tile), kind (tile table), stream (weights streamed layer by layer through two buffers)
-  //   prologue()                  epilogue threads, before the first tile
-  //   build(s, tile)              epilogue threads: first B operand of the tile
+  //   ntiles, NL (layers per tile), kind (tile table), stream (weights streamed layer by layer through two buffers),
+  //   side_build (the side warpgroup builds the first operand of every tile and consumes its last accumulator)
+  //   prologue()                  before the first tile (epilogue threads; edge phase: epilogue + side threads)
+  //   build(s, tile)              epilogue threads: first B operand of the tile            (!side_build)
+  //   side_first(s, tile), side_gather(s, tile), side_coords(s, tile), side_meta(s, tile)  (side_build)
   //   epi(s, tile, w)             epilogue threads: consume the accumulator of layer w (and write the next B operand)
   //   wimg(w)                     image offset of the weights of layer w (stream only)
   //   a_col(q, w), K(w)           MMA operand position / depth for layer w at stream position q
@@ -489,18 +548,54 @@ struct EngineTC {
     const int ntiles = p.ntiles, NL = p.NL;
     const int npairs = (ntiles + 1) >> 1;
     const int total_q = npairs * NL;
-    if (is_epi) {
-      p.prologue();
-      if (p.stream) {
-        load_w<TCU>(p.wimg(0), TC_WCOL);
-        if (total_q > 1) load_w<TCU>(p.wimg(1 % NL), TC_WCOL + 128);
-      }
+    if (is_epi || (P::side_build && is_side)) p.prologue();
+    if (is_epi && p.stream) {
+      load_w<128>(p.wimg(0), TC_WCOL);
+      if (total_q > 1) load_w<128>(p.wimg(1 % NL), TC_WCOL + 128);
     }
+    if constexpr (P::side_build) {
+      if (is_epi || is_side) phase_bar();     // per-edge geometry and the cleared accumulators are visible
+    }
+    if (is_side) {
+      if constexpr (P::side_build) {
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          if (s >= ntiles) continue;
+          p.side_gather(s, s);
+          p.side_meta(s, s);
+          cp_async_wait<0>();
+          arrive(B_BUILT, s);
+        }
+#pragma unroll 1
+        for (int tile = 0; tile < ntiles; ++tile) {
+          const int s = tile & 1, ntile = tile + 2;
+          qbeg();
+          wait_bar(B_HEADS, s);
+          qend(P_SIDE_WAIT);
+          if (ntile < ntiles) p.side_gather(s, ntile);
+          qend(P_SIDE_GATHER);
+          p.side_coords(s, tile);
+          qend(P_SIDE_COORD);
+          if (ntile < ntiles) {
+            p.side_meta(s, ntile);
+            qend(P_SIDE_META);
+            cp_async_wait<0>();
+            arrive(B_BUILT, s);
+            qend(P_SIDE_CPWAIT);
+          }
+        }
+      }
+      return;
+    }
+    const int first_kind = P::side_build ? B_BUILT : B_READY;
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
       if (s >= ntiles) continue;
-      if (is_epi) { p.build(s, s); arrive_ready(s); }
-      else issue_mma(s, p.a_col(0, 0), p.K(0));
+      if (is_epi) {
+        if constexpr (!P::side_build) { p.build(s, s); arrive(B_READY, s); }
+      } else {
+        issue_mma(s, first_kind, p.a_col(0, 0), p.K(0), P::side_build);
+      }
     }
     int q = 0;
 #pragma unroll 1
@@ -515,102 +610,121 @@ struct EngineTC {
           const int ntile = tile + 2;
           if (is_epi) {
             // the weights two layers ahead go into the buffer that layer q's MMAs (complete once done[last slot]
-            // fires) have been reading: fetch them into registers before the wait, store after it
+            // fires) have been reading
             const bool do_w = p.stream && last_slot && q + 2 < total_q;
-#if TC_WPREFETCH
-            uint32_t wv[2][TCU / 4];
-            if (do_w) fetch_w<TCU>(p.wimg((w + 2) % NL), wv);
             wait_done(s);
-            if (do_w) { qbeg(); store_w<TCU>(wv, TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
-#else
-            wait_done(s);
-            if (do_w) { qbeg(); load_w<TCU>(p.wimg((w + 2) % NL), TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
-#endif
+            if (do_w) { qbeg(); load_w<128>(p.wimg((w + 2) % NL), TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
             p.epi(s, tile, w);
-            if (w < NL - 1) arrive_ready(s);
-            else if (ntile < ntiles) { p.build(s, ntile); arrive_ready(s); }
+            if (w < NL - 1) arrive(B_READY, s);
+            else if constexpr (P::side_build) arrive(B_HEADS, s);
+            else if (ntile < ntiles) { p.build(s, ntile); arrive(B_READY, s); }
           } else {
-            if (w < NL - 1) issue_mma(s, p.a_col(q + 1, w + 1), p.K(w + 1));
-            else if (ntile < ntiles) issue_mma(s, p.a_col(q + 1, 0), p.K(0));
+            if (w < NL - 1) issue_mma(s, B_READY, p.a_col(q + 1, w + 1), p.K(w + 1), false);
+            else if (ntile < ntiles) issue_mma(s, first_kind, p.a_col(q + 1, 0), p.K(0), P::side_build);
           }
         }
       }
     }
   }
 
-  // column metadata of a node tile (kinds TT_NODE1 / TT_NODE): row offset (node * ND + slot), primal masks, header
+  // column metadata of a node tile (kinds TT_NODE1 / TT_NODE): row offset (node * ND + slot) or -1, chunk words, header
   __device__ __forceinline__ void node_meta(int s, int kind, int tile) {
-    qbeg();
     epi_bar();     // every thread is done with the previous contents of slot s's metadata
     const uint32_t* tp = tile_ptr(kind, tile);
     if (tid < 128) {
-      const uint32_t w = __ldg(tp + tid);
-      TCW(colw)[s * 128 + tid] = w;
-      TCI(coloffR)[s * 128 + tid] = (w & CW_VALID) ? cw_gid(w) * ND + cw_q(w) : -1;
+#pragma unroll
+      for (int sb = 0; sb < SUB; ++sb) {
+        const uint32_t cw = __ldg(tp + sb * 16 + (tid >> 3));
+        int g, q;
+        const bool valid = col_of(cw, tid, g, q);
+        TCI(coloffR)[(s * SUB + sb) * 128 + tid] = valid ? g * ND + q : -1;
+      }
+    } else if (tid < 128 + 48) {
+      const uint32_t w = __ldg(tp + (tid - 128));
+      if (tid < 128 + 32) TCW(chw)[s * 32 + (tid - 128)] = w;
+      else TCW(hdr)[s * 16 + (tid - 160)] = w;
     }
-    meta_copy(s, tp);
     epi_bar();
-    qend(P_META);
   }
 
   // =============================================================================================================
-  // node phase 1: h_in = [h | tau] Wd + bd ; P_s = h_in We0[0:H] ; P_r = h_in We0[H:2H] + be0 ; P_h = h_in Wh0[U:U+H] + bh0
+  // node phase 1: h_in = [h | tau] Wd + bd  (fp32 to hB, pre-split bf16 rows to Himg) ; P_h = h_in Wh0[U:U+H] + bh0
   // =============================================================================================================
   struct NodePre {
     EngineTC& e;
     int b, ntiles, NL, kind;
     static constexpr bool stream = false;
+    static constexpr bool side_build = false;
     __device__ __forceinline__ uint32_t a_col(int, int w) const { return TC_WCOL + 64u * w; }
-    __device__ __forceinline__ int K(int) const { return TCH; }
+    __device__ __forceinline__ int K(int) const { return KN; }
     __device__ __forceinline__ int wimg(int) const { return 0; }
     __device__ __forceinline__ void prologue() {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const TcImgBlock& ib = e.img.blk[b];
-      if (e.tid < TCH) {
+      if (e.tid < H) {
         float cv = bp.bd[e.tid];
-        for (int k = 0; k < e.m.T; ++k) cv = fmaf(TCF(tau)[k], bp.Wd[(TCH + k) * TCH + e.tid], cv);
+        for (int k = 0; k < e.m.T; ++k) cv = fmaf(TCF(tau)[k], bp.Wd[(H + k) * H + e.tid], cv);
         TCF(cvec)[e.tid] = cv;
       }
-      e.template load_w<TCH>(ib.Wd, TC_WCOL);
-      e.template load_w<TCH>(ib.We0s, TC_WCOL + 64);
-      e.template load_w<TCH>(ib.We0r, TC_WCOL + 128);
-      if (NL > 3) e.template load_w<TCH>(ib.Wh0h, TC_WCOL + 192);
+      e.template load_w<KN>(ib.Wd, TC_WCOL);
+      if (NL > 1) e.template load_w<KN>(ib.Wh0h, TC_WCOL + 64);
     }
     __device__ __forceinline__ void build(int s, int tile) {
       const KernelArgs& a = e.a;
+      e.qbeg();
       e.node_meta(s, kind, tile);
-      float v[64];
-      const float* src = e.hA() + e.f;
-      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
+      if (e.fu < H) {
+        float v[64];
+        const float* src = e.hA() + e.fu;
+        const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const int ro = ro_[c];
-        const float x = src[(size_t)(ro >= 0 && e.f < TCH ? ro : 0) * TCH];
-        v[c] = (ro >= 0 && e.f < TCH) ? x : 0.f;
+        for (int c = 0; c < 64; ++c) {
+          const int ro = ro_[c];
+          const float x = src[(size_t)(ro >= 0 ? ro : 0) * H];
+          v[c] = ro >= 0 ? x : 0.f;
+        }
+        e.write_B(s, v, e.sub * H + e.fu);
       }
-      if (e.f < TCH) e.write_B(s, v);
+      e.qend(P_NBUILD);
     }
     __device__ __forceinline__ void epi(int s, int, int w) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       float v[64];
-      const float cv = TCF(cvec)[e.f & (TCH - 1)];
-      const float bias = w == 0 ? cv : (w == 1 ? 0.f : (w == 2 ? bp.be[0][e.f] : bp.bh[0][e.f]));
       e.ld_acc(s, v);
-      const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
-      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
-      const bool act = (w > 0) || (e.f < TCH);
-      const int ld = w == 0 ? TCH : TCU;
-      float* dst = (w == 0 ? e.hB() : w == 1 ? e.Ps() : w == 2 ? e.Pr() : e.Ph()) + e.f;
+      const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
+      if (w == 0) {
+        if (e.fu >= H) return;      // lanes beyond the H outputs of h_in
+        const float bias = TCF(cvec)[e.fu];
+        float* dst = e.hB() + e.fu;
+        unsigned char* himg = e.Himg() + 2 * e.fu;
+        const bool dense = (kind == TT_NODE1);              // every column a primal row (first block / no divergence)
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-        v[c] += pr ? bias : 0.f;
-        const int ro = ro_[c];
-        if (ro >= 0 && act) dst[(size_t)ro * ld] = v[c];    // a repeated primal column rewrites the same value
+        for (int c = 0; c < 64; ++c) {
+          const bool pr = dense || (c & 7) == 0;            // bias on primal columns only
+          v[c] += pr ? bias : 0.f;
+          const int ro = ro_[c];
+          if (ro >= 0) {       // a repeated primal column rewrites the same values
+            dst[(size_t)ro * H] = v[c];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v[c]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v[c] - __bfloat162float(hi));
+            *reinterpret_cast<__nv_bfloat16*>(himg + (size_t)ro * ROWB) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(himg + (size_t)ro * ROWB + 2 * H) = lo;
+          }
+        }
+        if (NL > 1) e.write_B(s, v, e.sub * H + e.fu);
+      } else {
+        const float bias = bp.bh[0][e.fu];
+        float* dst = e.Ph() + e.fu;
+        const bool dense = (kind == TT_NODE1);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const bool pr = dense || (c & 7) == 0;
+          const int ro = ro_[c];
+          if (ro >= 0) dst[(size_t)ro * U] = v[c] + (pr ? bias : 0.f);
+        }
       }
-      if (w == 0 && e.f < TCH) e.write_B(s, v);
     }
   };
 
@@ -622,8 +736,9 @@ struct EngineTC {
     int b, ntiles, NL, kind;
     bool htan;
     static constexpr bool stream = true;
+    static constexpr bool side_build = false;
     __device__ __forceinline__ uint32_t a_col(int q, int) const { return TC_WCOL + 128u * (q & 1); }
-    __device__ __forceinline__ int K(int) const { return TCU; }
+    __device__ __forceinline__ int K(int) const { return 128; }
     __device__ __forceinline__ void prologue() {}
     __device__ __forceinline__ int wimg(int w) const {
       const TcImgBlock& ib = e.img.blk[b];
@@ -632,27 +747,31 @@ struct EngineTC {
     }
     __device__ __forceinline__ void build(int s, int tile) {
       const KernelArgs& a = e.a;
+      e.qbeg();
       e.node_meta(s, kind, tile);
       float v[64];
-      const float* src = e.Mg() + e.f;
-      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
+      const float* src = e.Mg() + e.fu;
+      const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const int ro = ro_[c];
-        const float x = src[(size_t)(ro >= 0 ? ro : 0) * TCU];
-        v[c] = ro >= 0 ? x : 0.f;
+      for (int cb = 0; cb < 64; cb += 16) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int ro = ro_[cb + u];
+          const float x = src[(size_t)(ro >= 0 ? ro : 0) * U];
+          v[cb + u] = ro >= 0 ? x : 0.f;
+        }
       }
-      e.write_B(s, v);
+      e.write_B(s, v, e.f);
+      e.qend(P_NBUILD);
     }
     __device__ __forceinline__ void epi(int s, int, int w) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int L = e.m.L;
-      const int* ro_ = TCI(coloffR) + s * 128 + 64 * e.hh;
+      const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
       float v[64];
       if (w == 0) {
-        const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
-        const float* ph = e.Ph() + e.f;
+        const float* ph = e.Ph() + e.fu;
         // + P_h (primal always; tangent columns where h_in carries tangents)
         e.ld_acc(s, v);
 #pragma unroll
@@ -661,46 +780,44 @@ struct EngineTC {
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const int c = cb + u;
-            const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
+            const bool pr = DIV ? ((c & 7) == 0) : true;
             const int ro = ro_[c];
             const bool use = ro >= 0 && (pr || htan);
-            const float x = ph[(size_t)(use ? ro : 0) * TCU];
+            const float x = ph[(size_t)(use ? ro : 0) * U];
             pv[u] = use ? x : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 16; ++u) v[cb + u] += pv[u];
         }
-        e.act_rule(v, 0.f, s);
-        e.write_B(s, v);
+        e.template act_rule<false>(v, 0.f, s, 0.f);
+        e.write_B(s, v, e.f);
       } else if (w < L) {
-        const float bias = bp.bh[w][e.f];
+        const float bias = bp.bh[w][e.fu];
         e.ld_acc(s, v);
-        e.act_rule(v, bias, s);
-        e.write_B(s, v);
+        e.template act_rule<false>(v, bias, s, 0.f);
+        e.write_B(s, v, e.f);
       } else {
-        const uint32_t m0 = TCW(pm)[s * 4 + 2 * e.hh], m1 = TCW(pm)[s * 4 + 2 * e.hh + 1];
-        const float bias = bp.bh[L][e.f & (TCH - 1)];
-        const float* hin = e.hB() + (e.f & (TCH - 1));
-        float* dst = e.hA() + e.f;
+        if (e.fu >= H) return;
+        const float bias = bp.bh[L][e.fu];
+        const float* hin = e.hB() + e.fu;
+        float* dst = e.hA() + e.fu;
         e.ld_acc(s, v);
-        if (e.f < TCH) {
 #pragma unroll
-          for (int cb = 0; cb < 64; cb += 16) {
-            float hv[16];
+        for (int cb = 0; cb < 64; cb += 16) {
+          float hv[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const int c = cb + u;
-              const bool pr = (((c < 32 ? m0 : m1) >> (c & 31)) & 1u) != 0u;
-              const int ro = ro_[c];
-              const bool use = ro >= 0 && (pr || htan);
-              const float x = hin[(size_t)(use ? ro : 0) * TCH];
-              hv[u] = (use ? x : 0.f) + (pr ? bias : 0.f);
-            }
+          for (int u = 0; u < 16; ++u) {
+            const int c = cb + u;
+            const bool pr = DIV ? ((c & 7) == 0) : true;
+            const int ro = ro_[c];
+            const bool use = ro >= 0 && (pr || htan);
+            const float x = hin[(size_t)(use ? ro : 0) * H];
+            hv[u] = (use ? x : 0.f) + (pr ? bias : 0.f);
+          }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const int ro = ro_[cb + u];
-              if (ro >= 0) dst[(size_t)ro * TCH] = v[cb + u] + hv[u];
-            }
+          for (int u = 0; u < 16; ++u) {
+            const int ro = ro_[cb + u];
+            if (ro >= 0) dst[(size_t)ro * H] = v[cb + u] + hv[u];
           }
         }
       }
@@ -708,305 +825,356 @@ struct EngineTC {
   };
 
   // =============================================================================================================
-  // edge phase: phi_e (layer 0 by gather) -> {attention gate + message aggregation, phi_x -> coordinate update}
+  // edge phase: phi_e (layer 0 = MMA on the gathered h_in rows) -> {attention gate + message aggregation,
+  //             phi_x -> coordinate update}
   // =============================================================================================================
   struct EdgePh {
     EngineTC& e;
-    int b, ntiles, NL, kind;   // kind = tile table (TT_FIRST / TT_MID / TT_LAST)
+    int b, ntiles, NL, kind;   // kind = tile table (TT_FIRST / TT_MID / TT_LAST / TT_EDGE1)
     bool htan, want_msg;       // want_msg: the aggregated messages feed phi_h (every block but the last)
     float wdf, waf, wpf;       // my feature's entry of w_d (|v|^2 column of phi_e layer 0), attention and head weights
     static constexpr bool stream = true;
+    static constexpr bool side_build = true;
     __device__ __forceinline__ uint32_t a_col(int q, int) const { return TC_WCOL + 128u * (q & 1); }
-    __device__ __forceinline__ int K(int) const { return TCU; }
+    __device__ __forceinline__ int K(int) const { return 128; }
     __device__ __forceinline__ int ekind() const { return kind == TT_FIRST ? KIND_FIRST : kind == TT_MID ? KIND_MID : KIND_LAST; }   // TT_EDGE1 has no tangent columns: the value is never used
     __device__ __forceinline__ int wimg(int w) const {
       const TcImgBlock& ib = e.img.blk[b];
       const int L = e.m.L;
-      return w < L - 1 ? ib.We[w + 1] : ib.Wx[w - (L - 1)];
+      return w == 0 ? ib.We0 : (w < L ? ib.We[w] : ib.Wx[w - L]);
     }
-    __device__ __forceinline__ void prologue() {
+    __device__ __forceinline__ void prologue() {      // epilogue + side threads (384)
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int n = e.n, dim = e.dim, D = e.D;
-      wdf = bp.We[0][(size_t)2 * TCH * TCU + e.f];
-      waf = bp.wa[e.f];
-      wpf = bp.wp[e.f];
-      for (int i = e.tid; i < D; i += TC_EPI) { TCF(xacc)[i] = 0.f; TCF(dacc)[i] = 0.f; }
+      constexpr int NTH = TC_EPI + TC_SIDE;
+      if (e.is_epi) {
+        wdf = bp.We[0][(size_t)2 * H * U + e.fu];
+        waf = bp.wa[e.fu];
+        wpf = bp.wp[e.fu];
+      }
+      for (int i = e.tid; i < D; i += NTH) { TCF(xacc)[i] = 0.f; TCF(dacc)[i] = 0.f; }
       if (DIV && kind != TT_LAST)
-        for (int i = e.tid; i < D * D; i += TC_EPI) TCF(xtacc)[i] = 0.f;
+        for (int i = e.tid; i < D * D; i += NTH) TCF(xtacc)[i] = 0.f;
       if (want_msg)
-        for (int i = e.tid; i < 2 * (a.lay.mrows + 1) * TCU; i += TC_EPI) TCF(macc)[i] = 0.f;
-      // per-edge geometry (egnn.py:73-76, numerical.py:7-10)
-      for (int ed = e.tid; ed < e.E; ed += TC_EPI) {
+        for (int i = e.tid; i < 2 * SUB * (a.lay.mrows + 1) * U; i += NTH) TCF(macc)[i] = 0.f;
+      // per-edge geometry (egnn.py:73)
+      for (int ed = e.tid; ed < e.E; ed += NTH) {
         const int i = ed / (n - 1), jj = ed - i * (n - 1);
         int j = i + 1 + jj; if (j >= n) j -= n;
-        float sq = 0.f;
-        for (int c = 0; c < dim; ++c) {
-          const float vv = TCF(xs)[i * dim + c] - TCF(xs)[j * dim + c];
-          TCF(egv)[ed * 3 + c] = vv;
-          sq = fmaf(vv, vv, sq);
-        }
-        const int isz = (sq == 0.f);
-        const float s1 = isz ? 1.f : sq;
-        const float len = sqrtf(s1);
-        TCI(egiz)[ed] = isz; TCF(egs1)[ed] = s1; TCF(eglen)[ed] = len; TCF(eginv)[ed] = 1.f / (e.m.C + len);
+        for (int c = 0; c < 3; ++c) TCF(egv)[ed * 3 + c] = c < dim ? TCF(xs)[i * dim + c] - TCF(xs)[j * dim + c] : 0.f;
       }
-      // the first tile's metadata pass starts with a barrier
     }
-    // per-column metadata of an edge tile
-    __device__ __forceinline__ void meta(int s, int tile) {
+    // (i, j) of an edge, its squared length with the safe rule (numerical.py:7-10)
+    __device__ __forceinline__ void edge_geo(int ed, int& i, int& j, float& sq) const {
       const KernelArgs& a = e.a;
-      const int n = e.n, dim = e.dim, D = e.D, ND = e.ND;
-      e.qbeg();
-      e.epi_bar();
+      const int n = e.n;
+      i = ed / (n - 1);
+      j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
+      const float v0 = TCF(egv)[ed * 3], v1 = TCF(egv)[ed * 3 + 1], v2 = TCF(egv)[ed * 3 + 2];
+      sq = fmaf(v2, v2, fmaf(v1, v1, v0 * v0));
+    }
+
+    // ---- side warpgroup: one thread per tile column (x SUB sub-tiles) ---------------------------------------------------
+    // B operand of phi_e layer 0 for `tile`: [h_in[sender] | h_in[receiver]] rows, K-major, by 16-byte cp.async copies
+    __device__ __forceinline__ void side_gather(int s, int tile) {
+      const KernelArgs& a = e.a;
+      const int n = e.n, ND = e.ND;
       const uint32_t* tp = e.tile_ptr(kind, tile);
-      if (e.tid < 128) {
-        const uint32_t w = __ldg(tp + e.tid);
-        const int win = (int)__ldg(tp + 192 + TH_WIN);
-        int oS = n * ND * TCU, oR = n * ND * TCU, mr = a.lay.mrows * TCU, ijk = 0;     // default: the zero rows
-        float sd = 0.f;
-        if (w & CW_VALID) {
-          const int ed = cw_gid(w), q = cw_q(w);
-          const int i = ed / (n - 1), jj = ed - i * (n - 1);
-          int j = i + 1 + jj; if (j >= n) j -= n;
-          int slot = 0, k = 0;
-          if (q == 0) {
-            sd = TCF(egs1)[ed];
-          } else {
-            k = dirmap(ekind(), q - 1, i, j, dim);
-            slot = 1 + k;
-            float acc = 0.f;
-            for (int c = 0; c < dim; ++c)
-              acc = fmaf(TCF(egv)[ed * 3 + c], TCF(xt)[(i * dim + c) * D + k] - TCF(xt)[(j * dim + c) * D + k], acc);
-            sd = TCI(egiz)[ed] ? 0.f : 2.f * acc;
-          }
-          if (q == 0 || htan) { oS = (j * ND + slot) * TCU; oR = (i * ND + slot) * TCU; }
-          if (!(w & CW_DUP) && want_msg) mr = ((i - win) * ND + slot) * TCU;
-          ijk = i | (j << 5) | (k << 10);
+      const unsigned char* himg = e.Himg();
+#pragma unroll 1
+      for (int item = e.tid - TC_EPI; item < SUB * 128; item += TC_SIDE) {
+        const int sb = item >> 7, c = item & 127;
+        unsigned char* bbase = smem_tc + a.lay.bop + s * TC_BOP + (c >> 3) * (int)TC_SBO_K + (c & 7) * 16;
+        const uint32_t cw = __ldg(tp + sb * 16 + (c >> 3));
+        int ed, q;
+        const bool valid = e.col_of(cw, c, ed, q);
+        int rs = n * ND, rr = n * ND;        // the all-zero row
+        if (valid && (q == 0 || htan)) {
+          const int i = ed / (n - 1);
+          int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
+          const int slot = q == 0 ? 0 : 1 + dirmap(ekind(), q - 1, i, j, e.dim);
+          rs = j * ND + slot; rr = i * ND + slot;
         }
-        TCW(colw)[s * 128 + e.tid] = w;
-        TCI(coloffS)[s * 128 + e.tid] = oS;
-        TCI(coloffR)[s * 128 + e.tid] = oR;
-        TCF(colsd)[s * 128 + e.tid] = sd;
-        TCI(colmrow)[s * 128 + e.tid] = mr;
-        TCI(colijk)[s * 128 + e.tid] = ijk;
+        const unsigned char* src_s = himg + (size_t)rs * ROWB;
+        const unsigned char* src_r = himg + (size_t)rr * ROWB;
+        // K rows of this sub-tile: [sb * 2H, +H) sender features, [sb * 2H + H, +H) receiver features
+        unsigned char* d0 = bbase + ((sb * 2 * H) >> 3) * (int)TC_LBO_K;
+#pragma unroll
+        for (int g = 0; g < H / 8; ++g) {
+          cp_async16(d0 + g * (int)TC_LBO_K, src_s + 16 * g);                                   // hi, sender
+          cp_async16(d0 + 32768 + g * (int)TC_LBO_K, src_s + 2 * H + 16 * g);                   // lo, sender
+          cp_async16(d0 + (H / 8 + g) * (int)TC_LBO_K, src_r + 16 * g);                         // hi, receiver
+          cp_async16(d0 + 32768 + (H / 8 + g) * (int)TC_LBO_K, src_r + 2 * H + 16 * g);         // lo, receiver
+        }
       }
-      e.meta_copy(s, tp);
-      e.epi_bar();
-      e.qend(P_META);
+      cp_async_commit();
     }
-    // phi_e layer 0 by gather: z0 = P_s[j] + P_r[i] + (|v|^2 or its tangent) w_d, then the activation rule
-    __device__ __forceinline__ void build(int s, int tile) {
+    // per-column tables of `tile` for the epilogue threads: |v|^2 (or its tangent), message-accumulator row
+    __device__ __forceinline__ void side_meta(int s, int tile) {
       const KernelArgs& a = e.a;
-      meta(s, tile);
-      e.qbeg();
-      float v[64];
-      const float* ps = e.Ps() + e.f;
-      const float* pr = e.Pr() + e.f;
-#pragma unroll
-      for (int cb = 0; cb < 64; cb += 16) {
-        float pa[16], pb[16];
-        const int c0 = s * 128 + 64 * e.hh + cb;
-#pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const int4 oS = reinterpret_cast<const int4*>(TCI(coloffS) + c0)[u4], oR = reinterpret_cast<const int4*>(TCI(coloffR) + c0)[u4];
-          pa[4 * u4] = ps[oS.x]; pa[4 * u4 + 1] = ps[oS.y]; pa[4 * u4 + 2] = ps[oS.z]; pa[4 * u4 + 3] = ps[oS.w];
-          pb[4 * u4] = pr[oR.x]; pb[4 * u4 + 1] = pr[oR.y]; pb[4 * u4 + 2] = pr[oR.z]; pb[4 * u4 + 3] = pr[oR.w];
+      const int sc = e.tid - TC_EPI, n = e.n, dim = e.dim, D = e.D, ND = e.ND;
+      const uint32_t* tp = e.tile_ptr(kind, tile);
+      const int win_i = (int)__ldg(tp + 32 + TH_WIN_I), win_s = (int)__ldg(tp + 32 + TH_WIN_S), win_ns = (int)__ldg(tp + 32 + TH_WIN_NS);
+      const int dump = a.lay.mrows * U;
+#pragma unroll 1
+      for (int item = sc; item < SUB * 128; item += TC_SIDE) {
+        const int sb = item >> 7, c = item & 127;
+        const uint32_t cw = __ldg(tp + sb * 16 + (c >> 3));
+        int ed, q;
+        const bool valid = e.col_of(cw, c, ed, q);
+        float sd = 0.f;
+        int mr = dump;
+        if (valid) {
+          int i, j; float sq;
+          edge_geo(ed, i, j, sq);
+          const bool isz = (sq == 0.f);
+          int gslot = 0;
+          if (q == 0) {
+            sd = isz ? 1.f : sq;
+          } else {
+            const int k = dirmap(ekind(), q - 1, i, j, dim);
+            gslot = 1 + k;
+            float acc = 0.f;
+            for (int cc = 0; cc < dim; ++cc)
+              acc = fmaf(TCF(egv)[ed * 3 + cc], TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k], acc);
+            sd = isz ? 0.f : 2.f * acc;
+          }
+          if (want_msg && !((c & 7) == 0 && DIV && !(cw & CH_OWNER))) {      // a repeated primal column contributes nothing
+            if (kind == TT_FIRST) {
+              const int u = c & 7;
+              if (u <= dim) mr = ((i - win_i) * (1 + dim) + u) * U;
+              else mr = -(1 + (i * ND + gslot));                              // per-sender direction: written straight to M
+            } else if (kind == TT_EDGE1) {
+              mr = i * U;
+            } else {
+              mr = ((i - win_i) * win_ns + (gslot - win_s)) * U;
+            }
+          }
         }
+        TCF(colsd)[(s * SUB + sb) * 128 + c] = sd;
+        TCI(colmrow)[(s * SUB + sb) * 128 + c] = mr;
+      }
+      if (sc < 48) {
+        const uint32_t w = __ldg(tp + sc);
+        if (sc < 32) TCW(chw)[s * 32 + sc] = w;
+        else TCW(hdr)[s * 16 + (sc - 32)] = w;
+      }
+    }
+    // coordinate head + coordinate update (egnn.py:82-95) and its tangents, from the head dot products of the tile
+    __device__ __forceinline__ void side_coords(int s, int tile) {
+      const KernelArgs& a = e.a;
+      const EcnfBlockParams& bp = e.m.blk[b];
+      const int sc = e.tid - TC_EPI, n = e.n, dim = e.dim, D = e.D;
+      const int ek = ekind();
+      const float bpv = bp.bp[0];
+      float* cd = TCF(cdbuf);
+      // stage 1: the contribution of a column to each coordinate of its receiver
+#pragma unroll 1
+      for (int item = sc; item < SUB * 128; item += TC_SIDE) {
+        const int sb = item >> 7, c = item & 127;
+        const uint32_t cw = TCW(chw)[s * 32 + sb * 16 + (c >> 3)];
+        int ed, q;
+        const bool valid = e.col_of(cw, c, ed, q);
+        float val[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          int i, j; float sq;
+          edge_geo(ed, i, j, sq);
+          const bool isz = (sq == 0.f);
+          const float len = sqrtf(isz ? 1.f : sq), inv = 1.f / (e.m.C + len);
+          const int h2 = c >> 6, cl = c & 63;
+          if (q == 0) {
+            const float pg = e.full_dot(s, h2, sb, cl) + bpv;
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const float4 sd = reinterpret_cast<const float4*>(TCF(colsd) + c0)[u4];
-          v[cb + 4 * u4] = fmaf(sd.x, wdf, pa[4 * u4] + pb[4 * u4]);
-          v[cb + 4 * u4 + 1] = fmaf(sd.y, wdf, pa[4 * u4 + 1] + pb[4 * u4 + 1]);
-          v[cb + 4 * u4 + 2] = fmaf(sd.z, wdf, pa[4 * u4 + 2] + pb[4 * u4 + 2]);
-          v[cb + 4 * u4 + 3] = fmaf(sd.w, wdf, pa[4 * u4 + 3] + pb[4 * u4 + 3]);
+            for (int cc = 0; cc < 3; ++cc) val[cc] = pg * TCF(egv)[ed * 3 + cc] * inv;
+          } else {
+            const int k = dirmap(ek, q - 1, i, j, dim);
+            const float pg = e.full_dot(s, h2, sb, cl & ~7) + bpv, pdv = e.full_dot(s, h2, sb, cl);
+            const float ld = isz ? 0.f : TCF(colsd)[(s * SUB + sb) * 128 + c] / (2.f * len);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              if (cc < dim) {
+                const float vc = TCF(egv)[ed * 3 + cc];
+                const float vd = TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k];
+                val[cc] = (pdv * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
+              }
+            }
+          }
+        }
+        cd[(sb * 128 + c) * 3] = val[0]; cd[(sb * 128 + c) * 3 + 1] = val[1]; cd[(sb * 128 + c) * 3 + 2] = val[2];
+      }
+      e.side_bar();
+      // stage 2: fixed-order sums over the chunks of a run (the edges of one receiver), one thread per (column position, coordinate)
+      const int P = e.hdr(s, TH_P);
+      if constexpr (!DIV) {
+        const int i_first = e.hdr(s, TH_IFIRST), i_last = e.hdr(s, TH_ILAST);
+        const int g0 = ch_gid(TCW(chw)[s * 32]);      // first edge of the tile (dense chunks, chunk p = 8 consecutive edges)
+        for (int idx = sc; idx < (i_last - i_first + 1) * dim; idx += TC_SIDE) {
+          const int i = i_first + idx / dim, cc = idx % dim;
+          const int ea = max(g0, i * (n - 1)), eb = min(g0 + 8 * P, min((i + 1) * (n - 1), e.E));
+          float acc = 0.f;
+          for (int ed = ea; ed < eb; ++ed) {
+            const int lg = ed - g0, pch = lg >> 3;
+            const int sb = pch % SUB, col = ((pch / SUB) & 1) * 64 + (pch / (2 * SUB)) * 8 + (lg & 7);
+            acc += cd[(sb * 128 + col) * 3 + cc];
+          }
+          TCF(xacc)[i * dim + cc] += acc;
+        }
+      } else if (sc < 8 * dim) {
+        const int u = sc / dim, cc = sc - u * dim;
+        float acc = 0.f;
+#pragma unroll 1
+        for (int pch = 0; pch < P; ++pch) {
+          const int sb = pch % SUB, wi = sb * 16 + ((pch / SUB) & 1) * 8 + pch / (2 * SUB);
+          const uint32_t cw = TCW(chw)[s * 32 + wi];
+          const int col = ((pch / SUB) & 1) * 64 + (pch / (2 * SUB)) * 8 + u;
+          const bool valid = u < ch_cnt(cw);
+          const float val = valid ? cd[(sb * 128 + col) * 3 + cc] : 0.f;
+          const int ed = ch_gid(cw), i = ed / (n - 1);
+          if (ek == KIND_FIRST && u > dim) {         // per-sender direction: no sum over the receiver's edges
+            if (valid) {
+              int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
+              TCF(xtacc)[(i * dim + cc) * D + j * dim + (u - 1 - dim)] += val;
+            }
+            continue;
+          }
+          if (u == 0 && !(cw & CH_OWNER)) { /* repeated primal column */ } else acc += val;
+          if (cw & CH_RUNEND) {
+            if (valid) {
+              if (u == 0) { if (cw & CH_OWNER) TCF(xacc)[i * dim + cc] += acc; }
+              else if (ek == KIND_LAST) { if (u - 1 == cc) TCF(dacc)[i * dim + cc] += acc; }
+              else {
+                const int k = ek == KIND_MID ? ch_qb(cw) + u - 2 : i * dim + (u - 1);
+                TCF(xtacc)[(i * dim + cc) * D + k] += acc;
+              }
+            }
+            acc = 0.f;
+          }
         }
       }
-      e.qend(P_GATHER);
-      e.act_rule(v, 0.f, s);
-      e.write_B(s, v);
-      e.qend(P_BUILD);
+      e.side_bar();      // cdbuf is rewritten by the next tile
     }
+
+    // ---- epilogue threads ------------------------------------------------------------------------------------------------
     __device__ __forceinline__ void epi(int s, int tile, int w) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int L = e.m.L;
-      const float bias = w < L - 1 ? bp.be[w + 1][e.f] : bp.bx[w - (L - 1)][e.f];
       float v[64];
       e.qbeg();
+      if (w == 0) e.wait_bar(B_BUILT, s);      // the side warpgroup's per-column tables of this tile are visible to me
       e.ld_acc(s, v);
-      e.qend(P_EPI_LD);
-      e.act_rule(v, bias, s);
-      e.qend(P_EPI_ACT);
+      if (w == 0) e.template act_rule<true>(v, bp.be[0][e.fu], s, wdf);
+      else e.template act_rule<false>(v, w < L ? bp.be[w][e.fu] : bp.bx[w - L][e.fu], s, 0.f);
       if (w < NL - 1) {
-        e.write_B(s, v);
-        e.qend(P_EPI_ST);
-        if (w == L - 2 && want_msg) messages(s, v);
-        e.qend(P_MSG);
+        e.write_B(s, v, e.f);
+        e.qend(P_EPI);
+        if (w == L - 1 && want_msg) { messages(s, v); e.qend(P_MSG); }
       } else {
         e.qend(P_EPI);
-        coords(s, v);
-        e.qend(P_COORD);
+        e.warp_dot(v, wpf, TCF(pdot) + s * 512 + e.warp * 64);      // coordinate head partials for the side warpgroup
+        e.qend(P_HEAD);
       }
     }
     // attention gate + message aggregation (egnn.py:99-104) from the fp32 phi_e outputs in v
     __device__ __forceinline__ void messages(int s, const float (&v)[64]) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
-      const int hh = e.hh, lane = e.lane, warp = e.warp;
-      float* pd = TCF(pdot) + s * 512;
-      e.warp_dot(v, waf, pd + warp * 64);
+      const int hh = e.hh, lane = e.lane, warp = e.warp, sub = e.sub;
+      e.warp_dot(v, waf, TCF(pdot) + s * 512 + warp * 64);
       e.half_bar();
       {
+        // msg = m e,  msg-dot = m-dot e + m e (1 - e) (m-dot . wa): per column the coefficient of its own value (wA) and of
+        // its chunk's primal value (wB); columns that contribute nothing (repeated primal, padding) get zeros
         const float bav = bp.ba[0];
-        const float* p4 = pd + (4 * hh) * 64;
         float aco[2], bco[2];
+        const uint32_t cw = e.my_chw(s, lane >> 2);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = 2 * lane + u;
-          const uint32_t cw = TCW(colw)[s * 128 + 64 * hh + c];
-          const int pc = cw_pc(cw);
-          const float raw = (p4[c] + p4[64 + c]) + (p4[128 + c] + p4[192 + c]);
-          const float rawp = (p4[pc] + p4[64 + pc]) + (p4[128 + pc] + p4[192 + pc]);
-          const float eg = ecnf_sigmoid(rawp + bav);
-          aco[u] = eg;
-          bco[u] = (cw & CW_PRIMAL) ? 0.f : eg * (1.f - eg) * raw;
+        for (int u2 = 0; u2 < 2; ++u2) {
+          const int c = 2 * lane + u2, u = c & 7;
+          const bool valid = (cw & CH_VALID) && u < ch_cnt(cw);
+          const float raw = e.full_dot(s, hh, sub, c);
+          float eg;
+          if constexpr (DIV) eg = ecnf_sigmoid(e.full_dot(s, hh, sub, c & ~7) + bav);
+          else eg = ecnf_sigmoid(raw + bav);
+          const bool prim = !DIV || u == 0;
+          aco[u2] = !valid ? 0.f : (prim ? ((!DIV || (cw & CH_OWNER)) ? eg : 0.f) : eg);
+          bco[u2] = (!valid || prim) ? 0.f : eg * (1.f - eg) * raw;
         }
         *reinterpret_cast<float2*>(TCF(wA) + warp * 64 + 2 * lane) = make_float2(aco[0], aco[1]);
         *reinterpret_cast<float2*>(TCF(wB) + warp * 64 + 2 * lane) = make_float2(bco[0], bco[1]);
       }
       __syncwarp();
+      const int nc = e.my_nch(s);
+      float* mac = TCF(macc) + (size_t)(hh * SUB + sub) * (a.lay.mrows + 1) * U + e.fu;
+      const float* wa_ = TCF(wA) + warp * 64;
+      const int* mr_ = TCI(colmrow) + (s * SUB + sub) * 128 + 64 * hh;
       if constexpr (!DIV) {
         // msg = m e per edge column; the columns of one receiver are consecutive, so a running sum is added to the
         // receiver's accumulator row whenever the row changes (padding columns go to the dump row)
-        float* mac = TCF(macc) + (size_t)hh * (a.lay.mrows + 1) * TCU + e.f;
-        const float* wa_ = TCF(wA) + warp * 64;
-        const int* mr_ = TCI(colmrow) + s * 128 + 64 * hh;
         int cur = mr_[0];
         float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
-          const int mr = mr_[c];
-          if (mr != cur) { mac[cur] += acc; acc = 0.f; cur = mr; }
-          acc = fmaf(v[c], wa_[c], acc);
+          if (c < 8 * nc) {
+            const int mr = mr_[c];
+            if (mr != cur) { mac[cur] += acc; acc = 0.f; cur = mr; }
+            acc = fmaf(v[c], wa_[c], acc);
+          }
         }
         mac[cur] += acc;
       } else {
-        // msg = m e,  msg-dot = m-dot e + m e (1 - e) (m-dot . wa)   accumulated per (receiver, slot) row; columns
-        // that do not contribute (repeated primal, padding) go to the dump row
-        float* mac = TCF(macc) + (size_t)hh * (a.lay.mrows + 1) * TCU + e.f;
-        const float* wa_ = TCF(wA) + warp * 64;
         const float* wb_ = TCF(wB) + warp * 64;
-        const int* mr_ = TCI(colmrow) + s * 128 + 64 * hh;
-        const uint32_t segs = (TCW(hdr)[s * 16 + TH_SEGS] >> (8 * hh)) & 0xffu;
-        float curm = 0.f, eg = 0.f;
+        const float inv_sqrt_nb = rsqrtf((float)(e.n - 1));
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-          const bool st = ((segs >> ch) & 1u) != 0u;     // a new edge starts here: its primal message and gate
-          curm = st ? v[8 * ch] : curm;
-          eg = st ? wa_[8 * ch] : eg;
-          // the 8 columns of a chunk belong to one edge: distinct accumulator rows (padding shares the dump row), so
-          // the loads need not wait for the stores
-          const int4 ma = reinterpret_cast<const int4*>(mr_)[2 * ch], mb = reinterpret_cast<const int4*>(mr_)[2 * ch + 1];
-          const float4 wa4 = reinterpret_cast<const float4*>(wb_)[2 * ch], wb4 = reinterpret_cast<const float4*>(wb_)[2 * ch + 1];
-          const int mr[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-          const float wbv[8] = {wa4.x, wa4.y, wa4.z, wa4.w, wb4.x, wb4.y, wb4.z, wb4.w};
-          float x[8], old[8];
+          if (ch < nc) {
+            const float curm = v[8 * ch];
+            const float4 wa0 = reinterpret_cast<const float4*>(wa_)[2 * ch], wa1 = reinterpret_cast<const float4*>(wa_)[2 * ch + 1];
+            const float4 wb0 = reinterpret_cast<const float4*>(wb_)[2 * ch], wb1 = reinterpret_cast<const float4*>(wb_)[2 * ch + 1];
+            const float wav[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
+            const float wbv[8] = {wb0.x, wb0.y, wb0.z, wb0.w, wb1.x, wb1.y, wb1.z, wb1.w};
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            x[u] = fmaf(curm, wbv[u], v[8 * ch + u] * eg);
-            old[u] = mac[mr[u]];
+            for (int u = 0; u < 8; ++u) acc[u] = fmaf(v[8 * ch + u], wav[u], fmaf(curm, wbv[u], acc[u]));
+            if (e.my_chw(s, ch) & CH_GRPEND) {
+              // my last chunk of this run: add the run's partial sums to the accumulator rows of its columns (distinct rows;
+              // padding shares the dump row); a negative entry is a per-sender row of the first block, stored straight to M
+              const int4 ma = reinterpret_cast<const int4*>(mr_)[2 * ch], mb = reinterpret_cast<const int4*>(mr_)[2 * ch + 1];
+              const int mr[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+              float old[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) old[u] = mac[mr[u] >= 0 ? mr[u] : a.lay.mrows * U];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (mr[u] >= 0) mac[mr[u]] = old[u] + acc[u];
+                else e.Mg()[(size_t)(-1 - mr[u]) * U + e.fu] = acc[u] * inv_sqrt_nb;
+                acc[u] = 0.f;
+              }
+            }
           }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) mac[mr[u]] = old[u] + x[u];
         }
       }
       if (e.hdr(s, TH_FLUSH)) {
-        // the receiver window is complete: write its aggregate to global (coalesced) and clear the accumulators
+        // the window is complete: write its aggregate to global (coalesced) and clear the accumulators
         e.epi_bar();
-        const int win = e.hdr(s, TH_WIN);
-        const int nrecv = min(a.lay.mrows / e.ND, e.n - win);
-        const int rows = nrecv * e.ND;
+        const int win_i = e.hdr(s, TH_WIN_I), win_nr = e.hdr(s, TH_WIN_NR), win_s = e.hdr(s, TH_WIN_S), win_ns = e.hdr(s, TH_WIN_NS);
+        const int rows = win_nr * win_ns;
         const float inv_sqrt_nb = rsqrtf((float)(e.n - 1));
-        float* m0p = TCF(macc) + e.f;
-        float* m1p = m0p + (size_t)(a.lay.mrows + 1) * TCU;
-        float* dst = e.Mg() + (size_t)win * e.ND * TCU + e.f;
-        for (int rr = hh; rr < rows; rr += 2) {
-          dst[(size_t)rr * TCU] = (m0p[rr * TCU] + m1p[rr * TCU]) * inv_sqrt_nb;
-          m0p[rr * TCU] = 0.f;
-          m1p[rr * TCU] = 0.f;
+        const size_t cstride = (size_t)(a.lay.mrows + 1) * U;
+        float* m0p = TCF(macc) + e.fu;
+        constexpr int RG = TC_EPI / U;       // row groups handled in parallel
+        for (int rr = e.tid / U; rr < rows; rr += RG) {
+          const int wi = rr / win_ns, ws = rr - wi * win_ns, i = win_i + wi;
+          const int gslot = (kind == TT_FIRST) ? (ws == 0 ? 0 : 1 + i * e.dim + (ws - 1)) : win_s + ws;
+          float sum = 0.f;
+#pragma unroll
+          for (int cp = 0; cp < 2 * SUB; ++cp) { sum += m0p[cp * cstride + rr * U]; m0p[cp * cstride + rr * U] = 0.f; }
+          e.Mg()[((size_t)i * e.ND + gslot) * U + e.fu] = sum * inv_sqrt_nb;
         }
-      }
-    }
-    // coordinate head + coordinate update (egnn.py:82-95) and its tangents
-    __device__ __forceinline__ void coords(int s, const float (&v)[64]) {
-      const KernelArgs& a = e.a;
-      const EcnfBlockParams& bp = e.m.blk[b];
-      const int n = e.n, dim = e.dim, D = e.D;
-      const int ek = ekind();
-      float* pd = TCF(pdot) + s * 512;
-      e.warp_dot(v, wpf, pd + e.warp * 64);
-      e.half_bar();
-      const float bpv = bp.bp[0];
-      float* cd = TCF(cdbuf) + s * 384;
-      // stage 1: one (column, coordinate) contribution per thread
-      for (int cc = 0; cc < dim; ++cc) {
-        const int col = 64 * e.hh + (e.f & 63);     // a column of my own half (only its partial dots are complete)
-        if ((e.f >> 6) != (cc & 1)) continue;       // the two 64-thread groups of a half alternate over the coordinates
-        const uint32_t cw = TCW(colw)[s * 128 + col];
-        float val = 0.f;
-        if ((cw & CW_VALID) && !(cw & CW_DUP)) {
-          const int ed = cw_gid(cw), q = cw_q(cw);
-          const int ijk = TCI(colijk)[s * 128 + col];
-          const int i = ijk & 31, j = (ijk >> 5) & 31, k = ijk >> 10;
-          const float* p4 = pd + (4 * (col >> 6)) * 64;
-          const int cl = col & 63, pc = cw_pc(cw);
-          const float pg = (p4[pc] + p4[64 + pc]) + (p4[128 + pc] + p4[192 + pc]) + bpv;
-          const float vc = TCF(egv)[ed * 3 + cc], inv = TCF(eginv)[ed];
-          if (q == 0) {
-            val = pg * vc * inv;
-          } else if (ek != KIND_LAST || k == i * dim + cc) {
-            const float pdv = (p4[cl] + p4[64 + cl]) + (p4[128 + cl] + p4[192 + cl]);
-            const float vd = TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k];
-            const float ld = TCI(egiz)[ed] ? 0.f : TCF(colsd)[s * 128 + col] / (2.f * TCF(eglen)[ed]);
-            val = (pdv * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
-          }
-        }
-        cd[col * 3 + cc] = val;
-      }
-      e.epi_bar();
-      {
-        // stage 2: fixed-order sums over the edges of a receiver
-        const int r = !DIV ? 1 : ek == KIND_MID ? e.ND : ek == KIND_LAST ? 1 + dim : 1 + 2 * dim;
-        const int g0 = e.hdr(s, TH_G0), ng = e.hdr(s, TH_NG), i_first = e.hdr(s, TH_IFIRST), i_last = e.hdr(s, TH_ILAST);
-        const int per = r * dim;
-        for (int idx = e.tid; idx < (i_last - i_first + 1) * per; idx += TC_EPI) {
-          const int ri = idx / per, rem = idx - ri * per, q = rem / dim, cc = rem - q * dim;
-          const int i = i_first + ri;
-          if (ek == KIND_LAST && q != 0 && q - 1 != cc) continue;
-          const int ga = max(g0, i * (n - 1)) - g0, gb = min(g0 + ng, (i + 1) * (n - 1)) - g0;
-          const bool per_sender = (ek == KIND_FIRST && q > dim);
-          float acc = 0.f;
-          for (int lg = ga; lg < gb; ++lg) {
-            int col = lg;       // primal-only tiles pack densely: column = local group index
-            if constexpr (DIV) {
-              const uint32_t gw = TCW(grpw)[s * 64 + lg];
-              const int qsplit = (int)(gw & 255u), colA = (int)((gw >> 8) & 255u), colB = (int)((gw >> 16) & 255u);
-              col = q < qsplit ? colA + q : colB + 1 + (q - qsplit);
-            }
-            const float val = cd[col * 3 + cc];
-            if (per_sender) {
-              const int ed = g0 + lg, jj = ed - i * (n - 1);
-              int j = i + 1 + jj; if (j >= n) j -= n;
-              TCF(xtacc)[(i * dim + cc) * D + j * dim + (q - 1 - dim)] += val;
-            } else {
-              acc += val;
-            }
-          }
-          if (q == 0) TCF(xacc)[i * dim + cc] += acc;
-          else if (ek == KIND_LAST) TCF(dacc)[i * dim + cc] += acc;
-          else if (!per_sender) TCF(xtacc)[(i * dim + cc) * D + (ek == KIND_MID ? q - 1 : i * dim + q - 1)] += acc;
-        }
+        e.epi_bar();
       }
     }
   };
@@ -1054,20 +1222,20 @@ struct EngineTC {
       const int ekind = !DIV ? TT_EDGE1 : last ? TT_LAST : (b == 0 ? TT_FIRST : TT_MID);
       const int nkind = DIV ? TT_NODE : TT_NODE1;
       pbeg();
-      {
+      if (!is_side) {
         const int kind = htan ? TT_NODE : TT_NODE1;
-        NodePre p{*this, b, a.tabs.cnt[kind], last ? 3 : 4, kind};
+        NodePre p{*this, b, a.tabs.cnt[kind], last ? 1 : 2, kind};
         run_phase(p);
       }
-      if (is_epi) epi_bar();     // P_s / P_r / P_h / h_in of every node are in global memory
+      if (is_epi || is_side) phase_bar();     // h_in (fp32 and pre-split rows) / P_h of every node are in global memory
       pend(P_NODE_PRE);
       {
-        EdgePh p{*this, b, a.tabs.cnt[ekind], 2 * m.L - 1, ekind, htan, !last, 0.f, 0.f, 0.f};
+        EdgePh p{*this, b, a.tabs.cnt[ekind], 2 * m.L, ekind, htan, !last, 0.f, 0.f, 0.f};
         run_phase(p);
       }
-      if (is_epi) epi_bar();     // coordinate accumulators and aggregated messages complete
+      if (is_epi || is_side) phase_bar();     // coordinate accumulators and aggregated messages complete
       pend(P_EDGE);
-      if (!last) {
+      if (!last && !is_side) {
         NodePost p{*this, b, a.tabs.cnt[nkind], m.L + 1, nkind, htan};
         run_phase(p);
       }
@@ -1077,8 +1245,8 @@ struct EngineTC {
         for (int i = tid; i < D; i += TC_EPI) TCF(xs)[i] += TCF(xacc)[i] * invnb;
         if (DIV && !last)
           for (int i = tid; i < D * D; i += TC_EPI) TCF(xt)[i] += TCF(xtacc)[i] * invnb;
-        epi_bar();
       }
+      if (is_epi || is_side) phase_bar();
       pend(P_NODE_POST);
     }
     if (is_epi) {
@@ -1095,21 +1263,23 @@ struct EngineTC {
   }
 };
 
-template <bool DIV>
+template <int U, int H, bool DIV>
 __global__ void __launch_bounds__(TC_NT, 1) ecnf_solve_tc_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ long long s_traj;
   __shared__ float s_ctl[8];
-  EngineTC<DIV> eng(a);
-  solve_body<EngineTC<DIV>, DIV>(a, eng, s_traj, s_ctl);
+  EngineTC<U, H, DIV> eng(a);
+  solve_body<EngineTC<U, H, DIV>, DIV>(a, eng, s_traj, s_ctl);
   eng.finish(reinterpret_cast<long long*>(reinterpret_cast<char*>(a.counter) + 64));
 }
 
-// ---- weight images: fp32 [K][N] (flax kernel) -> bf16 hi | lo, 128 lanes (out features; zero rows beyond N), two
-// consecutive k per 32-bit word, 4 words per 16-byte chunk:  uint4 index = (part * K/8 + chunk) * 128 + lane -----------
+// ---- weight images: fp32 [K][N] (flax kernel) -> bf16 hi | lo over 128 TMEM lanes, block-diagonal over `nsub` sub-tiles
+// (lane = sub * lane_stride + out feature, k = sub * ksub + in feature; zero elsewhere), two consecutive k per 32-bit
+// word, 4 words per 16-byte chunk:  uint4 index = (part * K/8 + chunk) * 128 + lane,  K = nsub * ksub ---------------------
 struct TcPrepItem {
   int src_off;   // floats, into the parameter buffer
   int dst_off;   // bytes, into the image buffer
-  int K, N;
+  int ksub, N;   // rows / columns of the source matrix
+  int nsub, lane_stride;
 };
 struct TcPrepList {
   int count;
@@ -1119,25 +1289,28 @@ struct TcPrepList {
 __global__ void tc_prep_kernel(const float* __restrict__ params, unsigned char* __restrict__ image, const TcPrepList list) {
   const TcPrepItem it = list.item[blockIdx.y];
   uint32_t* dst = reinterpret_cast<uint32_t*>(image + it.dst_off);
-  const int words = it.K / 2;                 // per lane and part
+  const int K = it.nsub * it.ksub;
+  const int words = K / 2;                 // per lane and part
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * words; idx += gridDim.x * blockDim.x) {
     const int wd = idx / 128, lane = idx - wd * 128;
+    const int sl = lane / it.lane_stride, o = lane - sl * it.lane_stride;
+    const int k0 = 2 * wd, sk = k0 / it.ksub, kk = k0 - sk * it.ksub;      // ksub is even: both k of a word share a sub-tile
     float x0 = 0.f, x1 = 0.f;
-    if (lane < it.N) {
-      x0 = params[it.src_off + (size_t)(2 * wd) * it.N + lane];
-      x1 = params[it.src_off + (size_t)(2 * wd + 1) * it.N + lane];
+    if (sl == sk && sl < it.nsub && o < it.N) {
+      x0 = params[it.src_off + (size_t)kk * it.N + o];
+      x1 = params[it.src_off + (size_t)(kk + 1) * it.N + o];
     }
     uint32_t h, l;
     split_pack(x0, x1, h, l);
-    const size_t o = ((size_t)(wd >> 2) * 128 + lane) * 4 + (wd & 3);
-    dst[o] = h;
-    dst[(size_t)(it.K / 8) * 128 * 4 + o] = l;
+    const size_t oo = ((size_t)(wd >> 2) * 128 + lane) * 4 + (wd & 3);
+    dst[oo] = h;
+    dst[(size_t)(K / 8) * 128 * 4 + oo] = l;
   }
 }
 
-__global__ void tc_tables_kernel(uint32_t* __restrict__ out, int n, int dim, TcTabs tabs) {
+__global__ void tc_tables_kernel(uint32_t* __restrict__ out, int n, int dim, int SUB, int MR, TcTabs tabs) {
   const int k = threadIdx.x;
-  if (k < TT_COUNT) tc_pack(k, n, dim, out + (size_t)tabs.off[k] * TC_TILE_WORDS);
+  if (k < TT_COUNT) tc_pack(k, n, dim, SUB, MR, out + (size_t)tabs.off[k] * TC_TILE_WORDS);
 }
 
 #undef TCF

@@ -1,9 +1,12 @@
 """Host-side invariants of the tensor-core engine's tile tables (ecnf_solve_tc.cuh: tc_pack), no GPU needed.
 
-The epilogue threads rely on them: every (group, slot) row appears exactly once (plus flagged repeats of a primal),
-segments are 'primal column, then its tangent columns' starting on 8-column chunk boundaries inside one 64-column half,
-the group words invert the column map, the header masks agree with the column words, and tiles of the message-passing
-kinds never span two receiver windows."""
+The kernel relies on them: a tile is 16 (x2 sub-tiles for U = 64) chunks of 8 columns; a chunk is one primal row of a
+group plus up to 7 of its tangent rows (slots qb .. qb+cnt-2), or 8 primal rows of consecutive groups (dense kinds); every
+(group, slot) row appears exactly once (the primal of a group is repeated in each of its chunks, one of them flagged as
+owner); chunk p of a tile lives in sub-tile p % SUB, half (p / SUB) % 2, position p / (2 SUB); a run (the chunks whose
+contributions are summed before they touch an accumulator) is a contiguous chunk range of one (receiver, slot group) with
+its end and every thread group's last chunk flagged; tiles of the message-passing kinds never span two windows and the
+rows of a window fit the accumulator."""
 import ctypes as C
 
 import numpy as np
@@ -11,9 +14,10 @@ import pytest
 
 from ecnf_b200.engine import CnfConfig, Engine
 
-TILE_WORDS = 240
-VALID, PRIMAL, DUP = 1 << 31, 1 << 30, 1 << 29
-NC0, NC1, N, G0, NG, WIN, FLUSH, IFIRST, ILAST, SEGS = range(10)
+TILE_WORDS = 48
+VALID, GRPEND, OWNER, RUNEND = 1 << 31, 1 << 22, 1 << 23, 1 << 24
+N, FLUSH, WIN_I, WIN_NR, WIN_S, WIN_NS, NCH, IFIRST, ILAST, P, MR = 0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13
+NODE1, NODE, FIRST, MID, LAST, EDGE1 = range(6)
 
 
 def table(eng, kind):
@@ -24,58 +28,93 @@ def table(eng, kind):
     return buf.reshape(cnt, TILE_WORDS)
 
 
-@pytest.mark.parametrize("n,dim", [(13, 3), (4, 2), (2, 2), (7, 3)])
-def test_tile_tables(n, dim):
-    eng = Engine(CnfConfig(n, dim, 0.01, 1.0, 3, (128, 128, 128), 64, 8, 1))
-    D, ND = n * dim, 1 + n * dim
-    rs = {0: 1, 1: ND, 2: 1 + 2 * dim, 3: ND, 4: 1 + dim, 5: 1}     # 5 = primal-only edge rows (sample_cnf, no divergence)
+def word_index(p, sub):
+    return (p % sub) * 16 + ((p // sub) % 2) * 8 + p // (2 * sub)
+
+
+SHAPES = [(13, 3, 128, 64), (4, 2, 128, 64), (2, 2, 128, 64), (7, 3, 128, 64), (22, 3, 64, 32), (5, 3, 64, 32), (9, 2, 64, 32)]
+
+
+@pytest.mark.parametrize("n,dim,U,H", SHAPES)
+def test_tile_tables(n, dim, U, H):
+    eng = Engine(CnfConfig(n, dim, 0.01, 1.0, 3, (U,) * 2, H, 8, 1))
+    SUB = 128 // U
+    D, ND, nb = n * dim, 1 + n * dim, n - 1
+    rs = {NODE1: 1, NODE: ND, FIRST: 1 + 2 * dim, MID: ND, LAST: 1 + dim, EDGE1: 1}
     for kind in range(6):
         tab = table(eng, kind)
         assert len(tab) > 0
-        r, ngroups = rs[kind], (n if kind < 2 else n * (n - 1))
-        seen = set()
+        r, ngroups = rs[kind], (n if kind < 2 else n * nb)
+        seen, owners = set(), set()
         for t in tab:
-            cols, grp, h = t[:128], t[128:192], t[192:208].astype(np.int64)
-            assert h[N] % 16 == 0 and 16 <= h[N] <= 128
-            assert h[N] >= (64 + h[NC1] if h[NC1] else h[NC0])
-            segs = 0
-            for half in range(2):
-                cur_g, cur_pc, last_q = -1, -1, -1
-                for c in range(64):
-                    w = int(cols[64 * half + c])
-                    if not (w & VALID):
-                        assert w == 0
-                        continue
-                    assert c < h[NC0 + half]
-                    g, q, pc = w & 1023, (w >> 10) & 255, (w >> 18) & 63
-                    if w & PRIMAL:
-                        assert q == 0 and pc == c
-                        if kind not in (0, 5):
-                            assert c % 8 == 0                      # chunk-aligned segment start
-                            segs |= 1 << (8 * half + c // 8)
-                        cur_g, cur_pc, last_q = g, c, 0
-                    else:
-                        assert g == cur_g and pc == cur_pc and q > last_q   # tangents follow their primal, same half
-                        last_q = q
-                    if not (w & DUP):
-                        assert (g, q) not in seen
-                        seen.add((g, q))
-                        lg = g - h[G0]
-                        assert 0 <= lg < h[NG]
-                        if kind in (0, 5):
-                            assert lg == 64 * half + c     # dense packing: column = local group index
-                        if lg < 64:
-                            gw = int(grp[lg])
-                            qs, ca, cb = gw & 255, (gw >> 8) & 255, (gw >> 16) & 255
-                            assert (ca + q if q < qs else cb + 1 + q - qs) == 64 * half + c
-                    mask = int(t[224 + (64 * half + c) // 32])
-                    assert bool(mask >> ((64 * half + c) % 32) & 1) == bool(w & PRIMAL)
-            if kind not in (0, 5):
-                assert h[SEGS] == segs
-            if kind in (2, 3):   # one receiver window per tile
-                rw = max(1, 40 // ND)
-                rw = min(rw, n)
-                assert h[IFIRST] // rw == h[ILAST] // rw == h[WIN] // rw and h[WIN] % rw == 0
-        assert len(seen) == ngroups * r
-        if kind in (2, 3, 5):
-            assert tab[-1][192 + FLUSH] == 1
+            h = t[32:48].astype(np.int64)
+            npch = int(h[P])
+            assert 1 <= npch <= 16 * SUB
+            used = {word_index(p, SUB) for p in range(npch)}
+            for wi in range(32):
+                assert bool(t[wi] & VALID) == (wi in used)
+            # header: chunk counts per (sub, half) and the MMA N
+            for sb in range(SUB):
+                for hh in range(2):
+                    want = sum(1 for p in range(npch) if p % SUB == sb and (p // SUB) % 2 == hh)
+                    assert h[NCH + sb * 2 + hh] == want
+            n0 = max(h[NCH + sb * 2] for sb in range(SUB))
+            n1 = max(h[NCH + sb * 2 + 1] for sb in range(SUB))
+            assert h[N] % 16 == 0 and 16 <= h[N] <= 128 and h[N] >= (64 + 8 * n1 if n1 else 8 * n0)
+            run_key, run_open = None, False
+            for p in range(npch):
+                w = int(t[word_index(p, SUB)])
+                gid, qb, cnt = w & 1023, (w >> 10) & 255, (w >> 18) & 15
+                assert 1 <= cnt <= 8
+                if r == 1:                                   # dense: 8 consecutive primal rows
+                    assert qb == 0
+                    for u in range(cnt):
+                        assert (gid + u, 0) not in seen
+                        seen.add((gid + u, 0))
+                    continue
+                assert qb >= 1 and (qb - 1) % 7 == 0 and cnt == 1 + min(7, r - qb)
+                assert bool(w & OWNER) == (qb == 1)
+                if w & OWNER:
+                    assert gid not in owners
+                    owners.add(gid)
+                    seen.add((gid, 0))
+                for u in range(1, cnt):
+                    assert (gid, qb + u - 1) not in seen
+                    seen.add((gid, qb + u - 1))
+                # runs: contiguous chunks of one (receiver, slot group)
+                i = gid // nb if kind >= FIRST else gid
+                key = (i, qb) if kind in (MID, LAST) else (gid, qb)
+                if run_open:
+                    assert key == run_key
+                run_key, run_open = key, not (w & RUNEND)
+            assert not run_open                              # a run never crosses a tile
+            # every thread group's last chunk of a run is flagged
+            start = 0
+            for p in range(npch):
+                if int(t[word_index(p, SUB)]) & RUNEND:
+                    for q in range(start, p + 1):
+                        flagged = bool(int(t[word_index(q, SUB)]) & GRPEND)
+                        assert flagged == (q + 2 * SUB > p)
+                    start = p + 1
+            if kind in (FIRST, MID):
+                rows = h[WIN_NR] * h[WIN_NS]
+                assert rows <= h[MR] and 8 <= h[MR]
+                assert h[WIN_I] <= h[IFIRST] <= h[ILAST] < h[WIN_I] + h[WIN_NR]
+                if kind == MID:
+                    for p in range(npch):
+                        w = int(t[word_index(p, SUB)])
+                        qb, cnt = (w >> 10) & 255, (w >> 18) & 15
+                        lo = 0 if (w & OWNER) else qb
+                        assert h[WIN_S] <= lo and qb + cnt - 2 < h[WIN_S] + h[WIN_NS]
+        assert len(seen) == ngroups * r, (kind, len(seen), ngroups * r)
+        if r > 1:
+            assert len(owners) == ngroups
+        if kind in (FIRST, MID, EDGE1):
+            assert tab[-1][32 + FLUSH] == 1
+
+
+def test_tensor_core_eligibility():
+    """(128, 64) and (64, 32) run on the tcgen05 engine for every shipped system size; (256, 32) does not."""
+    for n, dim, U, H, want in [(13, 3, 128, 64, True), (4, 2, 128, 64, True), (22, 3, 64, 32, True), (19, 3, 256, 32, False)]:
+        eng = Engine(CnfConfig(n, dim, 0.01, 1.0, 3, (U,) * 2, H, 8, 1))
+        assert (eng.lib.ecnf_solve_tensor_flops_per_eval(eng.handle) > 0) == want, (n, dim, U, H)
