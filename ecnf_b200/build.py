@@ -12,15 +12,17 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = PKG / "build"
-LIB = PKG / "libecnf_b200.so"
+# the per-phase cycle-counter build (ECNF_TC_PROFILE=1, tools/tc_profile.py) lives beside the product library
+_PROF = bool(os.environ.get("ECNF_TC_PROFILE"))
+OBJ = PKG / ("build_prof" if _PROF else "build")
+LIB = PKG / ("libecnf_b200_prof.so" if _PROF else "libecnf_b200.so")
 INCLUDE = PKG.parent / "include"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-diag-suppress", "177",
 ]
-if os.environ.get("ECNF_TC_PROFILE"):      # per-phase cycle counters in the tensor-core kernel (tools/tc_profile.py)
+if _PROF:
     NVCC_FLAGS.append("-DECNF_TC_PROFILE")
 
 

@@ -21,7 +21,7 @@ struct TcImages {
 
 // shared-memory carve-up of the tensor-core engine (byte offsets), computed on the host
 struct TcSmemLayout {
-  int bop, macc, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, colsd, colmrow, coloffR, chw, hdr, pdot, wA, wB, cdbuf,
+  int bop, macc, xt, xtacc, dacc, xs, xs0, xacc, mu, tau, cvec, ode, red, colsd, colmrow, chw, hdr, pdot, pdh, wA, wB, cdbuf,
       egv, bars, prof, total_bytes;
   int mrows;   // rows of the message accumulator (one window of receivers x slots)
 };

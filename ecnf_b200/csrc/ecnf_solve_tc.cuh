@@ -83,11 +83,14 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR
   int run_start = 0;     // first chunk (index in the tile) of the current run
   auto tp = [&](int t) { return out + (size_t)t * TC_TILE_WORDS; };
   auto word_index = [&](int q) { return (q % SUB) * 16 + ((q / SUB) % 2) * 8 + q / (2 * SUB); };
-  auto end_run = [&]() {       // chunks [run_start, p) form a run: mark its end and the last chunk of every thread group
+  // chunks [run_start, p) form a run (the chunks whose coordinate contributions are summed): mark its end (CH_RUNEND) and the
+  // last chunk of every thread group (CH_GRPEND: where the epilogue threads flush their message partial sums); each_chunk:
+  // every chunk flushes on its own (first block: the per-sender tangent rows)
+  auto end_run = [&](bool each_chunk = false) {
     if (out && p > run_start) {
       tp(tile)[word_index(p - 1)] |= CH_RUNEND;
       for (int q = run_start; q < p; ++q)
-        if (q + 2 * SUB >= p) tp(tile)[word_index(q)] |= CH_GRPEND;
+        if (each_chunk || q + 2 * SUB >= p) tp(tile)[word_index(q)] |= CH_GRPEND;
     }
     run_start = p;
   };
@@ -158,12 +161,13 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR
     int W = MR / rows_per; if (W < 1) W = 1; if (W > n) W = n;
     for (int i0 = 0; i0 < n; i0 += W) {
       win_i = i0; win_nr = (n - i0 < W) ? n - i0 : W; win_s = 0; win_ns = rows_per;
-      for (int i = i0; i < i0 + win_nr; ++i)
+      for (int i = i0; i < i0 + win_nr; ++i) {
         for (int e = i * nb; e < (i + 1) * nb; ++e) {
-          if (p == CAP) close(0);
+          if (p == CAP) { end_run(true); close(0); }
           put(e, 1, r, true);
-          end_run();                 // per-sender directions: every chunk is flushed on its own
         }
+        end_run(true);               // a run = the edges of one receiver; the message partial sums flush per chunk
+      }
       close(1);
     }
     return tile;
@@ -224,12 +228,13 @@ __host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim, int MR) {
   L.cvec = take(64 * 4);
   L.ode = take(11 * S * 4);
   L.red = take((S + 16) * 4);
-  L.colsd = take(2 * SUB * 128 * 4);
-  L.colmrow = take(2 * SUB * 128 * 4);
-  L.coloffR = take(2 * SUB * 128 * 4);
-  L.chw = take(2 * 32 * 4);
-  L.hdr = take(2 * 16 * 4);
-  L.pdot = take(2 * 8 * 64 * 4);
+  // per-tile tables: one buffer per (slot, tile parity) so that the side warps prepare a tile two tiles ahead of its use
+  L.colsd = take(4 * SUB * 128 * 4);
+  L.colmrow = take(4 * SUB * 128 * 4);     // node phases: row offset of a column (coloffR)
+  L.chw = take(4 * 32 * 4);
+  L.hdr = take(4 * 16 * 4);
+  L.pdot = take(2 * 8 * 64 * 4);           // attention-logit partials (consumed by the epilogue threads themselves)
+  L.pdh = take(4 * 8 * 64 * 4);            // coordinate-head partials per (slot, tile parity), consumed by the side warps
   L.wA = take(8 * 64 * 4);
   L.wB = take(8 * 64 * 4);
   L.cdbuf = take(SUB * 128 * 3 * 4);
@@ -277,7 +282,7 @@ struct EngineTC {
   uint32_t lane_addr;    // (32 * (warp & 3)) << 16
   uint32_t par;          // phase parities of the mbarriers this thread waits on: bit (kind * 2 + slot)
 
-  enum { B_READY = 0, B_DONE = 1, B_BUILT = 2, B_HEADS = 3 };
+  enum { B_READY = 0, B_DONE = 1, B_BUILT = 2, B_HEADS = 3, B_BFREE = 4 };
   enum { P_NODE_PRE, P_EDGE, P_NODE_POST, P_WAIT, P_EPI, P_MSG, P_HEAD, P_WLOAD, P_SIDE_WAIT, P_SIDE_GATHER, P_SIDE_COORD,
          P_SIDE_META, P_SIDE_CPWAIT, P_NBUILD, P_NCOUNT };
 #ifdef ECNF_TC_PROFILE
@@ -317,6 +322,7 @@ struct EngineTC {
       mbar_init(bar(B_DONE, 0), 1); mbar_init(bar(B_DONE, 1), 1);
       mbar_init(bar(B_BUILT, 0), TC_SIDE); mbar_init(bar(B_BUILT, 1), TC_SIDE);
       mbar_init(bar(B_HEADS, 0), TC_EPI); mbar_init(bar(B_HEADS, 1), TC_EPI);
+      mbar_init(bar(B_BFREE, 0), 1); mbar_init(bar(B_BFREE, 1), 1);
 #ifdef ECNF_TC_PROFILE
       for (int k = 0; k < P_NCOUNT; ++k) prof_s()[k] = 0;
 #endif
@@ -374,10 +380,15 @@ struct EngineTC {
   }
   // issue warp: wait for the producers, then acc[s] = W^T (TMEM columns a_col: hi [0, K/2), lo [K/2, K)) x B[s]
   // (K x N), 3-pass split; commit -> done[s].  kmajor: B is the gathered layer-0 operand.
-  __device__ __forceinline__ void issue_mma(int s, int wait_kind, uint32_t a_col, int K, bool kmajor) {
+  // tb: table buffer of the tile (slot * 2 + tile parity).  free_b: these are the last MMAs of the tile that read B[s] -- a
+  // second commit tells the side warps that the buffer can take the next tile's gathered operand.
+  // drained: additionally wait until the epilogue threads have read the previous tile's last accumulator out of acc[s].
+  __device__ __forceinline__ void issue_mma(int s, int tb, int wait_kind, uint32_t a_col, int K, bool kmajor, bool free_b,
+                                            bool drained = false) {
     if (lane == 0) {
+      if (drained) wait_bar(B_READY, s);
       wait_bar(wait_kind, s);
-      const int N = hdr(s, TH_N);
+      const int N = hdr(tb, TH_N);
       const uint32_t idesc = make_idesc_bf16(128, N) | (kmajor ? 0u : IDESC_B_MN);
       const uint32_t bsm = smem_u32(smem_tc + a.lay.bop) + (uint32_t)s * TC_BOP;
       const uint32_t lbo = kmajor ? TC_LBO_K : TC_LBO, sbo = kmajor ? TC_SBO_K : TC_SBO;
@@ -396,6 +407,7 @@ struct EngineTC {
         mma_ts(acc, a_hi, bl, idesc, 1u);
       }
       mma_commit(bar(B_DONE, s));
+      if (free_b) mma_commit(bar(B_BFREE, s));
     }
   }
 
@@ -422,43 +434,40 @@ struct EngineTC {
       *reinterpret_cast<uint4*>(base + 32768 + g8 * (int)TC_SBO) = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
-  __device__ __forceinline__ int hdr(int s, int k) const { return TCI(hdr)[s * 16 + k]; }
-  __device__ __forceinline__ int my_nch(int s) const { return hdr(s, TH_NCH + sub * 2 + hh); }   // chunks in use in my 64 columns
-  __device__ __forceinline__ uint32_t my_chw(int s, int ch) const { return TCW(chw)[s * 32 + sub * 16 + 8 * hh + ch]; }
+  // tile tables live in one buffer per (slot, tile parity):  tb = slot * 2 + ((tile >> 1) & 1)
+  __device__ __forceinline__ static int tb_of(int s, int tile) { return s * 2 + ((tile >> 1) & 1); }
+  __device__ __forceinline__ int hdr(int tb, int k) const { return TCI(hdr)[tb * 16 + k]; }
+  __device__ __forceinline__ int my_nch(int tb) const { return hdr(tb, TH_NCH + sub * 2 + hh); }   // chunks in use in my 64 columns
+  __device__ __forceinline__ uint32_t my_chw(int tb, int ch) const { return TCW(chw)[tb * 32 + sub * 16 + 8 * hh + ch]; }
   // Activation rule: a = silu(z + bias) on the primal column of every chunk, a-dot = silu'(z_primal) z-dot on the 7 tangent
   // columns behind it.  L0: z gets the rank-1 |v|^2 term of phi_e layer 0 first (sd = the tile's per-column table, wdf =
-  // my feature's entry of w_d).  Chunks beyond the used ones are zeroed (the MMA reads them).
+  // my feature's entry of w_d).  Branch-free over all 8 chunks: columns beyond the used ones hold finite stale values that
+  // no table refers to.
   template <bool L0>
-  __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int s, float wdf) {
-    const int nc = my_nch(s);
-    const float* sdp = TCF(colsd) + (s * SUB + sub) * 128 + 64 * hh;
+  __device__ __forceinline__ void act_rule(float (&v)[64], float bias, int tb, float wdf) {
+    const float* sdp = TCF(colsd) + (tb * SUB + sub) * 128 + 64 * hh;
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
-      if (ch < nc) {
-        if constexpr (L0) {
-          const float4 s0 = reinterpret_cast<const float4*>(sdp)[2 * ch], s1 = reinterpret_cast<const float4*>(sdp)[2 * ch + 1];
-          v[8 * ch] = fmaf(s0.x, wdf, v[8 * ch]); v[8 * ch + 1] = fmaf(s0.y, wdf, v[8 * ch + 1]);
-          v[8 * ch + 2] = fmaf(s0.z, wdf, v[8 * ch + 2]); v[8 * ch + 3] = fmaf(s0.w, wdf, v[8 * ch + 3]);
-          v[8 * ch + 4] = fmaf(s1.x, wdf, v[8 * ch + 4]); v[8 * ch + 5] = fmaf(s1.y, wdf, v[8 * ch + 5]);
-          v[8 * ch + 6] = fmaf(s1.z, wdf, v[8 * ch + 6]); v[8 * ch + 7] = fmaf(s1.w, wdf, v[8 * ch + 7]);
-        }
-        if constexpr (!DIV) {      // every column is a primal row
+      if constexpr (L0) {
+        const float4 s0 = reinterpret_cast<const float4*>(sdp)[2 * ch], s1 = reinterpret_cast<const float4*>(sdp)[2 * ch + 1];
+        v[8 * ch] = fmaf(s0.x, wdf, v[8 * ch]); v[8 * ch + 1] = fmaf(s0.y, wdf, v[8 * ch + 1]);
+        v[8 * ch + 2] = fmaf(s0.z, wdf, v[8 * ch + 2]); v[8 * ch + 3] = fmaf(s0.w, wdf, v[8 * ch + 3]);
+        v[8 * ch + 4] = fmaf(s1.x, wdf, v[8 * ch + 4]); v[8 * ch + 5] = fmaf(s1.y, wdf, v[8 * ch + 5]);
+        v[8 * ch + 6] = fmaf(s1.z, wdf, v[8 * ch + 6]); v[8 * ch + 7] = fmaf(s1.w, wdf, v[8 * ch + 7]);
+      }
+      if constexpr (!DIV) {      // every column is a primal row
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float z = v[8 * ch + u] + bias;
-            v[8 * ch + u] = z * fast_sigmoid(z);
-          }
-        } else {
-          const float z = v[8 * ch] + bias;
-          const float sg = fast_sigmoid(z);
-          const float cur = sg * (1.f + z * (1.f - sg));
-          v[8 * ch] = z * sg;
-#pragma unroll
-          for (int u = 1; u < 8; ++u) v[8 * ch + u] *= cur;
+        for (int u = 0; u < 8; ++u) {
+          const float z = v[8 * ch + u] + bias;
+          v[8 * ch + u] = z * fast_sigmoid(z);
         }
       } else {
+        const float z = v[8 * ch] + bias;
+        const float sg = fast_sigmoid(z);
+        const float cur = sg * (1.f + z * (1.f - sg));
+        v[8 * ch] = z * sg;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[8 * ch + u] = 0.f;
+        for (int u = 1; u < 8; ++u) v[8 * ch + u] *= cur;
       }
     }
   }
@@ -490,9 +499,9 @@ struct EngineTC {
     bfly_round<2>(x);
     *reinterpret_cast<float2*>(pd + 2 * lane) = make_float2(x[0], x[1]);
   }
-  // complete dot product of column c (0..63 of half h2) of sub-tile sb from the per-warp partials of slot s
-  __device__ __forceinline__ float full_dot(int s, int h2, int sb, int c) const {
-    const float* p4 = TCF(pdot) + s * 512 + (4 * h2) * 64 + c;
+  // complete dot product of column c (0..63 of half h2) of sub-tile sb from the 8 x 64 per-warp partials at pd
+  __device__ __forceinline__ float full_dot(const float* pd, int h2, int sb, int c) const {
+    const float* p4 = pd + (4 * h2) * 64 + c;
     if constexpr (SUB == 1) return (p4[0] + p4[64]) + (p4[128] + p4[192]);
     else return p4[(2 * sb) * 64] + p4[(2 * sb + 1) * 64];
   }
@@ -558,30 +567,47 @@ struct EngineTC {
     }
     if (is_side) {
       if constexpr (P::side_build) {
+        // tables run two tiles (per slot) ahead of their use; the gather of tile t + 2 starts as soon as the tensor core
+        // has finished reading B[s] for tile t; the coordinate update of tile t fills the time in between
 #pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          if (s >= ntiles) continue;
-          p.side_gather(s, s);
-          p.side_meta(s, s);
+        for (int t0 = 0; t0 < 2 && t0 < ntiles; ++t0) {
+          p.side_meta(tb_of(t0, t0), t0);
+          p.side_gather(t0, t0);
           cp_async_wait<0>();
-          arrive(B_BUILT, s);
+          arrive(B_BUILT, t0);
         }
 #pragma unroll 1
-        for (int tile = 0; tile < ntiles; ++tile) {
-          const int s = tile & 1, ntile = tile + 2;
+        for (int t0 = 2; t0 < 4 && t0 < ntiles; ++t0) p.side_meta(tb_of(t0 & 1, t0), t0);
+#pragma unroll 1
+        for (int pr = 0; pr < npairs; ++pr) {
           qbeg();
-          wait_bar(B_HEADS, s);
-          qend(P_SIDE_WAIT);
-          if (ntile < ntiles) p.side_gather(s, ntile);
-          qend(P_SIDE_GATHER);
-          p.side_coords(s, tile);
-          qend(P_SIDE_COORD);
-          if (ntile < ntiles) {
-            p.side_meta(s, ntile);
+#pragma unroll 1
+          for (int s = 0; s < 2; ++s) {        // the operands the epilogue threads will wait for come first
+            const int tile = 2 * pr + s, ntile = tile + 2;
+            if (tile >= ntiles) continue;
+            if (ntile < ntiles) {
+              wait_bar(B_BFREE, s);
+              qend(P_SIDE_WAIT);
+              p.side_gather(s, ntile);
+              qend(P_SIDE_GATHER);
+              cp_async_wait<0>();
+              qend(P_SIDE_CPWAIT);
+            }
+            // heads[s] of this tile is consumed BEFORE the next tile of the slot is released: the epilogue threads can
+            // then never complete a second phase of the barrier (tile + 2) before this wait (an mbarrier parity wait cannot
+            // tell phase k from phase k + 2)
+            wait_bar(B_HEADS, s);
+            qend(P_SIDE_WAIT);
+            if (ntile < ntiles) arrive(B_BUILT, s);
+          }
+#pragma unroll 1
+          for (int s = 0; s < 2; ++s) {
+            const int tile = 2 * pr + s;
+            if (tile >= ntiles) continue;
+            p.side_coords(tb_of(s, tile), tile);
+            qend(P_SIDE_COORD);
+            if (tile + 4 < ntiles) p.side_meta(tb_of(s, tile + 4), tile + 4);      // = this tile's table buffer, free now
             qend(P_SIDE_META);
-            cp_async_wait<0>();
-            arrive(B_BUILT, s);
-            qend(P_SIDE_CPWAIT);
           }
         }
       }
@@ -592,9 +618,9 @@ struct EngineTC {
     for (int s = 0; s < 2; ++s) {
       if (s >= ntiles) continue;
       if (is_epi) {
-        if constexpr (!P::side_build) { p.build(s, s); arrive(B_READY, s); }
+        if constexpr (!P::side_build) { p.build(s, tb_of(s, s), s); arrive(B_READY, s); }
       } else {
-        issue_mma(s, first_kind, p.a_col(0, 0), p.K(0), P::side_build);
+        issue_mma(s, tb_of(s, s), first_kind, p.a_col(0, 0), p.K(0), P::side_build, false);
       }
     }
     int q = 0;
@@ -608,19 +634,24 @@ struct EngineTC {
           if (tile >= ntiles) continue;
           const bool last_slot = (s == 1) || (tile + 1 >= ntiles);
           const int ntile = tile + 2;
+          const int tb = tb_of(s, tile);
           if (is_epi) {
             // the weights two layers ahead go into the buffer that layer q's MMAs (complete once done[last slot]
             // fires) have been reading
             const bool do_w = p.stream && last_slot && q + 2 < total_q;
             wait_done(s);
             if (do_w) { qbeg(); load_w<128>(p.wimg((w + 2) % NL), TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
-            p.epi(s, tile, w);
+            p.epi(s, tb, tile, w);
             if (w < NL - 1) arrive(B_READY, s);
             else if constexpr (P::side_build) arrive(B_HEADS, s);
-            else if (ntile < ntiles) { p.build(s, ntile); arrive(B_READY, s); }
+            else if (ntile < ntiles) { p.build(s, tb_of(s, ntile), ntile); arrive(B_READY, s); }
           } else {
-            if (w < NL - 1) issue_mma(s, B_READY, p.a_col(q + 1, w + 1), p.K(w + 1), false);
-            else if (ntile < ntiles) issue_mma(s, first_kind, p.a_col(q + 1, 0), p.K(0), P::side_build);
+            // the MMAs of layer NL - 1 are the last readers of B[s] for this tile
+            // (one B_BFREE commit per tile that has a successor in its slot: the side warps wait for exactly those)
+            if (w < NL - 1)
+              issue_mma(s, tb, B_READY, p.a_col(q + 1, w + 1), p.K(w + 1), false, P::side_build && w + 1 == NL - 1 && ntile < ntiles);
+            else if (ntile < ntiles)
+              issue_mma(s, tb_of(s, ntile), first_kind, p.a_col(q + 1, 0), p.K(0), P::side_build, false, P::side_build);
           }
         }
       }
@@ -628,8 +659,8 @@ struct EngineTC {
   }
 
   // column metadata of a node tile (kinds TT_NODE1 / TT_NODE): row offset (node * ND + slot) or -1, chunk words, header
-  __device__ __forceinline__ void node_meta(int s, int kind, int tile) {
-    epi_bar();     // every thread is done with the previous contents of slot s's metadata
+  __device__ __forceinline__ void node_meta(int tb, int kind, int tile) {
+    epi_bar();     // every thread is done with the previous contents of this table buffer
     const uint32_t* tp = tile_ptr(kind, tile);
     if (tid < 128) {
 #pragma unroll
@@ -637,12 +668,12 @@ struct EngineTC {
         const uint32_t cw = __ldg(tp + sb * 16 + (tid >> 3));
         int g, q;
         const bool valid = col_of(cw, tid, g, q);
-        TCI(coloffR)[(s * SUB + sb) * 128 + tid] = valid ? g * ND + q : -1;
+        TCI(colmrow)[(tb * SUB + sb) * 128 + tid] = valid ? g * ND + q : -1;
       }
     } else if (tid < 128 + 48) {
       const uint32_t w = __ldg(tp + (tid - 128));
-      if (tid < 128 + 32) TCW(chw)[s * 32 + (tid - 128)] = w;
-      else TCW(hdr)[s * 16 + (tid - 160)] = w;
+      if (tid < 128 + 32) TCW(chw)[tb * 32 + (tid - 128)] = w;
+      else TCW(hdr)[tb * 16 + (tid - 160)] = w;
     }
     epi_bar();
   }
@@ -670,14 +701,14 @@ struct EngineTC {
       e.template load_w<KN>(ib.Wd, TC_WCOL);
       if (NL > 1) e.template load_w<KN>(ib.Wh0h, TC_WCOL + 64);
     }
-    __device__ __forceinline__ void build(int s, int tile) {
+    __device__ __forceinline__ void build(int s, int tb, int tile) {
       const KernelArgs& a = e.a;
       e.qbeg();
-      e.node_meta(s, kind, tile);
+      e.node_meta(tb, kind, tile);
       if (e.fu < H) {
         float v[64];
         const float* src = e.hA() + e.fu;
-        const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
+        const int* ro_ = TCI(colmrow) + (tb * SUB + e.sub) * 128 + 64 * e.hh;
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
           const int ro = ro_[c];
@@ -688,12 +719,12 @@ struct EngineTC {
       }
       e.qend(P_NBUILD);
     }
-    __device__ __forceinline__ void epi(int s, int, int w) {
+    __device__ __forceinline__ void epi(int s, int tb, int, int w) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       float v[64];
       e.ld_acc(s, v);
-      const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
+      const int* ro_ = TCI(colmrow) + (tb * SUB + e.sub) * 128 + 64 * e.hh;
       if (w == 0) {
         if (e.fu >= H) return;      // lanes beyond the H outputs of h_in
         const float bias = TCF(cvec)[e.fu];
@@ -745,13 +776,13 @@ struct EngineTC {
       const int L = e.m.L;
       return w == 0 ? ib.Wh0m : (w < L ? ib.Wh[w] : ib.WhL);
     }
-    __device__ __forceinline__ void build(int s, int tile) {
+    __device__ __forceinline__ void build(int s, int tb, int tile) {
       const KernelArgs& a = e.a;
       e.qbeg();
-      e.node_meta(s, kind, tile);
+      e.node_meta(tb, kind, tile);
       float v[64];
       const float* src = e.Mg() + e.fu;
-      const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
+      const int* ro_ = TCI(colmrow) + (tb * SUB + e.sub) * 128 + 64 * e.hh;
 #pragma unroll
       for (int cb = 0; cb < 64; cb += 16) {
 #pragma unroll
@@ -764,11 +795,11 @@ struct EngineTC {
       e.write_B(s, v, e.f);
       e.qend(P_NBUILD);
     }
-    __device__ __forceinline__ void epi(int s, int, int w) {
+    __device__ __forceinline__ void epi(int s, int tb, int, int w) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int L = e.m.L;
-      const int* ro_ = TCI(coloffR) + (s * SUB + e.sub) * 128 + 64 * e.hh;
+      const int* ro_ = TCI(colmrow) + (tb * SUB + e.sub) * 128 + 64 * e.hh;
       float v[64];
       if (w == 0) {
         const float* ph = e.Ph() + e.fu;
@@ -789,12 +820,12 @@ struct EngineTC {
 #pragma unroll
           for (int u = 0; u < 16; ++u) v[cb + u] += pv[u];
         }
-        e.template act_rule<false>(v, 0.f, s, 0.f);
+        e.template act_rule<false>(v, 0.f, tb, 0.f);
         e.write_B(s, v, e.f);
       } else if (w < L) {
         const float bias = bp.bh[w][e.fu];
         e.ld_acc(s, v);
-        e.template act_rule<false>(v, bias, s, 0.f);
+        e.template act_rule<false>(v, bias, tb, 0.f);
         e.write_B(s, v, e.f);
       } else {
         if (e.fu >= H) return;
@@ -911,7 +942,7 @@ struct EngineTC {
       cp_async_commit();
     }
     // per-column tables of `tile` for the epilogue threads: |v|^2 (or its tangent), message-accumulator row
-    __device__ __forceinline__ void side_meta(int s, int tile) {
+    __device__ __forceinline__ void side_meta(int tb, int tile) {
       const KernelArgs& a = e.a;
       const int sc = e.tid - TC_EPI, n = e.n, dim = e.dim, D = e.D, ND = e.ND;
       const uint32_t* tp = e.tile_ptr(kind, tile);
@@ -952,28 +983,29 @@ struct EngineTC {
             }
           }
         }
-        TCF(colsd)[(s * SUB + sb) * 128 + c] = sd;
-        TCI(colmrow)[(s * SUB + sb) * 128 + c] = mr;
+        TCF(colsd)[(tb * SUB + sb) * 128 + c] = sd;
+        TCI(colmrow)[(tb * SUB + sb) * 128 + c] = mr;
       }
       if (sc < 48) {
         const uint32_t w = __ldg(tp + sc);
-        if (sc < 32) TCW(chw)[s * 32 + sc] = w;
-        else TCW(hdr)[s * 16 + (sc - 32)] = w;
+        if (sc < 32) TCW(chw)[tb * 32 + sc] = w;
+        else TCW(hdr)[tb * 16 + (sc - 32)] = w;
       }
     }
     // coordinate head + coordinate update (egnn.py:82-95) and its tangents, from the head dot products of the tile
-    __device__ __forceinline__ void side_coords(int s, int tile) {
+    __device__ __forceinline__ void side_coords(int tb, int tile) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int sc = e.tid - TC_EPI, n = e.n, dim = e.dim, D = e.D;
       const int ek = ekind();
       const float bpv = bp.bp[0];
       float* cd = TCF(cdbuf);
+      const float* pd = TCF(pdh) + tb * 512;
       // stage 1: the contribution of a column to each coordinate of its receiver
 #pragma unroll 1
       for (int item = sc; item < SUB * 128; item += TC_SIDE) {
         const int sb = item >> 7, c = item & 127;
-        const uint32_t cw = TCW(chw)[s * 32 + sb * 16 + (c >> 3)];
+        const uint32_t cw = TCW(chw)[tb * 32 + sb * 16 + (c >> 3)];
         int ed, q;
         const bool valid = e.col_of(cw, c, ed, q);
         float val[3] = {0.f, 0.f, 0.f};
@@ -984,13 +1016,13 @@ struct EngineTC {
           const float len = sqrtf(isz ? 1.f : sq), inv = 1.f / (e.m.C + len);
           const int h2 = c >> 6, cl = c & 63;
           if (q == 0) {
-            const float pg = e.full_dot(s, h2, sb, cl) + bpv;
+            const float pg = e.full_dot(pd, h2, sb, cl) + bpv;
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) val[cc] = pg * TCF(egv)[ed * 3 + cc] * inv;
           } else {
             const int k = dirmap(ek, q - 1, i, j, dim);
-            const float pg = e.full_dot(s, h2, sb, cl & ~7) + bpv, pdv = e.full_dot(s, h2, sb, cl);
-            const float ld = isz ? 0.f : TCF(colsd)[(s * SUB + sb) * 128 + c] / (2.f * len);
+            const float pg = e.full_dot(pd, h2, sb, cl & ~7) + bpv, pdv = e.full_dot(pd, h2, sb, cl);
+            const float ld = isz ? 0.f : TCF(colsd)[(tb * SUB + sb) * 128 + c] / (2.f * len);
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
               if (cc < dim) {
@@ -1004,11 +1036,11 @@ struct EngineTC {
         cd[(sb * 128 + c) * 3] = val[0]; cd[(sb * 128 + c) * 3 + 1] = val[1]; cd[(sb * 128 + c) * 3 + 2] = val[2];
       }
       e.side_bar();
-      // stage 2: fixed-order sums over the chunks of a run (the edges of one receiver), one thread per (column position, coordinate)
-      const int P = e.hdr(s, TH_P);
+      // stage 2: fixed-order sums over the chunks of a run (the edges of one receiver)
+      const int P = e.hdr(tb, TH_P);
       if constexpr (!DIV) {
-        const int i_first = e.hdr(s, TH_IFIRST), i_last = e.hdr(s, TH_ILAST);
-        const int g0 = ch_gid(TCW(chw)[s * 32]);      // first edge of the tile (dense chunks, chunk p = 8 consecutive edges)
+        const int i_first = e.hdr(tb, TH_IFIRST), i_last = e.hdr(tb, TH_ILAST);
+        const int g0 = ch_gid(TCW(chw)[tb * 32]);      // first edge of the tile (dense chunks, chunk p = 8 consecutive edges)
         for (int idx = sc; idx < (i_last - i_first + 1) * dim; idx += TC_SIDE) {
           const int i = i_first + idx / dim, cc = idx % dim;
           const int ea = max(g0, i * (n - 1)), eb = min(g0 + 8 * P, min((i + 1) * (n - 1), e.E));
@@ -1020,67 +1052,68 @@ struct EngineTC {
           }
           TCF(xacc)[i * dim + cc] += acc;
         }
-      } else if (sc < 8 * dim) {
-        const int u = sc / dim, cc = sc - u * dim;
-        float acc = 0.f;
+      } else {
+        // one work item per (chunk that ends a run, column position u, coordinate cc): walks back over the run's chunks
+        const int per = 8 * dim;
 #pragma unroll 1
-        for (int pch = 0; pch < P; ++pch) {
-          const int sb = pch % SUB, wi = sb * 16 + ((pch / SUB) & 1) * 8 + pch / (2 * SUB);
-          const uint32_t cw = TCW(chw)[s * 32 + wi];
-          const int col = ((pch / SUB) & 1) * 64 + (pch / (2 * SUB)) * 8 + u;
-          const bool valid = u < ch_cnt(cw);
-          const float val = valid ? cd[(sb * 128 + col) * 3 + cc] : 0.f;
+        for (int item = sc; item < P * per; item += TC_SIDE) {
+          const int pch = item / per, rem = item - pch * per, u = rem / dim, cc = rem - u * dim;
+          auto widx = [](int q) { return (q % SUB) * 16 + ((q / SUB) & 1) * 8 + q / (2 * SUB); };
+          auto colof = [&](int q) { return (q % SUB) * 128 + ((q / SUB) & 1) * 64 + (q / (2 * SUB)) * 8 + u; };
+          const uint32_t cw = TCW(chw)[tb * 32 + widx(pch)];
+          if (u >= ch_cnt(cw)) continue;
           const int ed = ch_gid(cw), i = ed / (n - 1);
-          if (ek == KIND_FIRST && u > dim) {         // per-sender direction: no sum over the receiver's edges
-            if (valid) {
-              int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
-              TCF(xtacc)[(i * dim + cc) * D + j * dim + (u - 1 - dim)] += val;
-            }
+          if (ek == KIND_FIRST && u > dim) {                       // per-sender direction: one entry per edge, no sum
+            int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
+            TCF(xtacc)[(i * dim + cc) * D + j * dim + (u - 1 - dim)] += cd[colof(pch) * 3 + cc];
             continue;
           }
-          if (u == 0 && !(cw & CH_OWNER)) { /* repeated primal column */ } else acc += val;
-          if (cw & CH_RUNEND) {
-            if (valid) {
-              if (u == 0) { if (cw & CH_OWNER) TCF(xacc)[i * dim + cc] += acc; }
-              else if (ek == KIND_LAST) { if (u - 1 == cc) TCF(dacc)[i * dim + cc] += acc; }
-              else {
-                const int k = ek == KIND_MID ? ch_qb(cw) + u - 2 : i * dim + (u - 1);
-                TCF(xtacc)[(i * dim + cc) * D + k] += acc;
-              }
-            }
-            acc = 0.f;
-          }
+          if (!(cw & CH_RUNEND)) continue;
+          if (u == 0 && !(cw & CH_OWNER)) continue;              // repeated primal columns
+          if (ek == KIND_LAST && u > 0 && u - 1 != cc) continue;   // only the Jacobian diagonal is needed in the last block
+          float acc = 0.f;
+          int q = pch;
+          do {
+            acc += cd[colof(q) * 3 + cc];
+            --q;
+          } while (q >= 0 && !(TCW(chw)[tb * 32 + widx(q)] & CH_RUNEND));
+          if (u == 0) TCF(xacc)[i * dim + cc] += acc;
+          else if (ek == KIND_LAST) TCF(dacc)[i * dim + cc] += acc;
+          else TCF(xtacc)[(i * dim + cc) * D + (ek == KIND_MID ? ch_qb(cw) + u - 2 : i * dim + (u - 1))] += acc;
         }
       }
       e.side_bar();      // cdbuf is rewritten by the next tile
     }
 
     // ---- epilogue threads ------------------------------------------------------------------------------------------------
-    __device__ __forceinline__ void epi(int s, int tile, int w) {
+    __device__ __forceinline__ void epi(int s, int tb, int tile, int w) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int L = e.m.L;
       float v[64];
       e.qbeg();
-      if (w == 0) e.wait_bar(B_BUILT, s);      // the side warpgroup's per-column tables of this tile are visible to me
+      if (w == 0) e.wait_bar(B_BUILT, s);      // the side warps' per-column tables of this tile are visible to me
       e.ld_acc(s, v);
-      if (w == 0) e.template act_rule<true>(v, bp.be[0][e.fu], s, wdf);
-      else e.template act_rule<false>(v, w < L ? bp.be[w][e.fu] : bp.bx[w - L][e.fu], s, 0.f);
+      // last layer: acc[s] is drained -- the next tile of this slot (its operand may already be gathered) can start
+      if (w == NL - 1 && tile + 2 < ntiles) e.arrive(B_READY, s);
+      if (w == 0) e.template act_rule<true>(v, bp.be[0][e.fu], tb, wdf);
+      else e.template act_rule<false>(v, w < L ? bp.be[w][e.fu] : bp.bx[w - L][e.fu], tb, 0.f);
       if (w < NL - 1) {
         e.write_B(s, v, e.f);
         e.qend(P_EPI);
-        if (w == L - 1 && want_msg) { messages(s, v); e.qend(P_MSG); }
+        if (w == L - 1 && want_msg) { messages(s, tb, v); e.qend(P_MSG); }
       } else {
         e.qend(P_EPI);
-        e.warp_dot(v, wpf, TCF(pdot) + s * 512 + e.warp * 64);      // coordinate head partials for the side warpgroup
+        e.warp_dot(v, wpf, TCF(pdh) + tb * 512 + e.warp * 64);      // coordinate head partials for the side warps
         e.qend(P_HEAD);
       }
     }
     // attention gate + message aggregation (egnn.py:99-104) from the fp32 phi_e outputs in v
-    __device__ __forceinline__ void messages(int s, const float (&v)[64]) {
+    __device__ __forceinline__ void messages(int s, int tb, const float (&v)[64]) {
       const KernelArgs& a = e.a;
       const EcnfBlockParams& bp = e.m.blk[b];
       const int hh = e.hh, lane = e.lane, warp = e.warp, sub = e.sub;
+      const float* pd = TCF(pdot) + s * 512;
       e.warp_dot(v, waf, TCF(pdot) + s * 512 + warp * 64);
       e.half_bar();
       {
@@ -1088,14 +1121,14 @@ struct EngineTC {
         // its chunk's primal value (wB); columns that contribute nothing (repeated primal, padding) get zeros
         const float bav = bp.ba[0];
         float aco[2], bco[2];
-        const uint32_t cw = e.my_chw(s, lane >> 2);
+        const uint32_t cw = e.my_chw(tb, lane >> 2);
 #pragma unroll
         for (int u2 = 0; u2 < 2; ++u2) {
           const int c = 2 * lane + u2, u = c & 7;
           const bool valid = (cw & CH_VALID) && u < ch_cnt(cw);
-          const float raw = e.full_dot(s, hh, sub, c);
+          const float raw = e.full_dot(pd, hh, sub, c);
           float eg;
-          if constexpr (DIV) eg = ecnf_sigmoid(e.full_dot(s, hh, sub, c & ~7) + bav);
+          if constexpr (DIV) eg = ecnf_sigmoid(e.full_dot(pd, hh, sub, c & ~7) + bav);
           else eg = ecnf_sigmoid(raw + bav);
           const bool prim = !DIV || u == 0;
           aco[u2] = !valid ? 0.f : (prim ? ((!DIV || (cw & CH_OWNER)) ? eg : 0.f) : eg);
@@ -1105,10 +1138,10 @@ struct EngineTC {
         *reinterpret_cast<float2*>(TCF(wB) + warp * 64 + 2 * lane) = make_float2(bco[0], bco[1]);
       }
       __syncwarp();
-      const int nc = e.my_nch(s);
+      const int nc = e.my_nch(tb);
       float* mac = TCF(macc) + (size_t)(hh * SUB + sub) * (a.lay.mrows + 1) * U + e.fu;
       const float* wa_ = TCF(wA) + warp * 64;
-      const int* mr_ = TCI(colmrow) + (s * SUB + sub) * 128 + 64 * hh;
+      const int* mr_ = TCI(colmrow) + (tb * SUB + sub) * 128 + 64 * hh;
       if constexpr (!DIV) {
         // msg = m e per edge column; the columns of one receiver are consecutive, so a running sum is added to the
         // receiver's accumulator row whenever the row changes (padding columns go to the dump row)
@@ -1139,7 +1172,7 @@ struct EngineTC {
             const float wbv[8] = {wb0.x, wb0.y, wb0.z, wb0.w, wb1.x, wb1.y, wb1.z, wb1.w};
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc[u] = fmaf(v[8 * ch + u], wav[u], fmaf(curm, wbv[u], acc[u]));
-            if (e.my_chw(s, ch) & CH_GRPEND) {
+            if (e.my_chw(tb, ch) & CH_GRPEND) {
               // my last chunk of this run: add the run's partial sums to the accumulator rows of its columns (distinct rows;
               // padding shares the dump row); a negative entry is a per-sender row of the first block, stored straight to M
               const int4 ma = reinterpret_cast<const int4*>(mr_)[2 * ch], mb = reinterpret_cast<const int4*>(mr_)[2 * ch + 1];
@@ -1157,10 +1190,10 @@ struct EngineTC {
           }
         }
       }
-      if (e.hdr(s, TH_FLUSH)) {
+      if (e.hdr(tb, TH_FLUSH)) {
         // the window is complete: write its aggregate to global (coalesced) and clear the accumulators
         e.epi_bar();
-        const int win_i = e.hdr(s, TH_WIN_I), win_nr = e.hdr(s, TH_WIN_NR), win_s = e.hdr(s, TH_WIN_S), win_ns = e.hdr(s, TH_WIN_NS);
+        const int win_i = e.hdr(tb, TH_WIN_I), win_nr = e.hdr(tb, TH_WIN_NR), win_s = e.hdr(tb, TH_WIN_S), win_ns = e.hdr(tb, TH_WIN_NS);
         const int rows = win_nr * win_ns;
         const float inv_sqrt_nb = rsqrtf((float)(e.n - 1));
         const size_t cstride = (size_t)(a.lay.mrows + 1) * U;

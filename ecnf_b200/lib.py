@@ -11,7 +11,8 @@ from pathlib import Path
 from typing import Optional
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libecnf_b200.so"
+# ECNF_B200_LIB: load another build of the same library (the cycle-counter build of tools/tc_profile.py)
+LIB_PATH = Path(os.environ["ECNF_B200_LIB"]) if os.environ.get("ECNF_B200_LIB") else PKG / "libecnf_b200.so"
 
 MODE_VF, MODE_VF_DIV, MODE_SAMPLE, MODE_SAMPLE_LOGQ, MODE_LOGPROB = range(5)
 TARGET_LJ, TARGET_DW = 0, 1

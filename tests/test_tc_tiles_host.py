@@ -83,7 +83,7 @@ def test_tile_tables(n, dim, U, H):
                     seen.add((gid, qb + u - 1))
                 # runs: contiguous chunks of one (receiver, slot group)
                 i = gid // nb if kind >= FIRST else gid
-                key = (i, qb) if kind in (MID, LAST) else (gid, qb)
+                key = (i, qb) if kind >= FIRST else (gid, qb)
                 if run_open:
                     assert key == run_key
                 run_key, run_open = key, not (w & RUNEND)
@@ -94,7 +94,7 @@ def test_tile_tables(n, dim, U, H):
                 if int(t[word_index(p, SUB)]) & RUNEND:
                     for q in range(start, p + 1):
                         flagged = bool(int(t[word_index(q, SUB)]) & GRPEND)
-                        assert flagged == (q + 2 * SUB > p)
+                        assert flagged == (kind == FIRST or q + 2 * SUB > p)      # first block: every chunk flushes
                     start = p + 1
             if kind in (FIRST, MID):
                 rows = h[WIN_NR] * h[WIN_NS]

@@ -25,7 +25,11 @@ def run_case(name):
     from ecnf_b200 import lib as L
     from ecnf_b200.engine import Engine
     from helpers import make_pair, rel_err
-    n, dim, blocks, units, H, nfeat = CASES[name]
+    if name in CASES:
+        n, dim, blocks, units, H, nfeat = CASES[name]
+    else:      # "n,dim,blocks,U,H,L"
+        n, dim, blocks, U_, H, L_ = (int(v) for v in name.split(","))
+        units, nfeat = (U_,) * L_, 1
     ocfg, flat, tree, ecfg = make_pair(n, dim, blocks, units, H, n_features=nfeat, head_variance=0.5)
     eng = Engine(ecfg)
     B = 5
@@ -46,6 +50,8 @@ def run_case(name):
         torch.cuda.synchronize()
         derr = np.abs(div.cpu().numpy() - div_ref.numpy()).max() / (np.abs(div_ref.numpy()).max() + 1.0)
         print(f"{name:12s} {tag} vf+div  rel err f {rel_err(f2.cpu().numpy(), f_ref.numpy()):.2e}  div {derr:.2e}", flush=True)
+    if os.environ.get("TC_CHECK_QUICK"):
+        return
     x0 = O.base_sample_from_noise(ocfg, torch.tensor(rng.standard_normal((B, n * dim)).astype(np.float32)))
     ctrl = L.make_ctrl(use_fixed_step_size=True, step_size=0.25)
     res = {}
@@ -84,7 +90,7 @@ if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)
     for nm in names:
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", nm], timeout=240, capture_output=True, text=True)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", nm], timeout=int(os.environ.get("TC_CHECK_TIMEOUT", "120")), capture_output=True, text=True)
             print(r.stdout, end="")
             if r.returncode != 0:
                 print(f"{nm}: exit {r.returncode}\n{r.stderr[-1500:]}", flush=True)
