@@ -52,7 +52,7 @@ __host__ __device__ __forceinline__ int ch_gid(uint32_t w) { return (int)(w & 10
 __host__ __device__ __forceinline__ int ch_qb(uint32_t w) { return (int)((w >> 10) & 255u); }    // slot of column 1 (0: dense chunk)
 __host__ __device__ __forceinline__ int ch_cnt(uint32_t w) { return (int)((w >> 18) & 15u); }     // valid columns, 1..8
 // header words (from word 32 of a tile)
-enum { TH_N = 0, TH_FLUSH, TH_WIN_I, TH_WIN_NR, TH_WIN_S, TH_WIN_NS, TH_NCH /* +sub*2+hh */, TH_IFIRST = 10, TH_ILAST, TH_P, TH_MR };
+enum { TH_N = 0, TH_FLUSH, TH_WIN_I, TH_WIN_NR, TH_WIN_S, TH_WIN_NS, TH_NCH /* +sub*2+hh */, TH_IFIRST = 10, TH_ILAST, TH_P, TH_MR, TH_RUNMASK };
 
 // sigmoid from ex2.approx / rcp.approx (5 instructions, ~1e-7 absolute: well inside the 3-pass GEMM error)
 __device__ __forceinline__ float fast_sigmoid(float z) {
@@ -115,6 +115,10 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR
       h[TH_FLUSH] = (uint32_t)flush;
       h[TH_WIN_I] = (uint32_t)win_i; h[TH_WIN_NR] = (uint32_t)win_nr; h[TH_WIN_S] = (uint32_t)win_s; h[TH_WIN_NS] = (uint32_t)win_ns;
       h[TH_IFIRST] = (uint32_t)i_first; h[TH_ILAST] = (uint32_t)i_last; h[TH_P] = (uint32_t)p; h[TH_MR] = (uint32_t)MR;
+      uint32_t rm = 0u;      // bit q: chunk q (sequence index) ends a run
+      for (int q = 0; q < p; ++q)
+        if (tp(tile)[word_index(q)] & CH_RUNEND) rm |= 1u << q;
+      h[TH_RUNMASK] = rm;
     }
     ++tile;
     p = 0; run_start = 0;
@@ -1053,22 +1057,32 @@ struct EngineTC {
           TCF(xacc)[i * dim + cc] += acc;
         }
       } else {
-        // one work item per (chunk that ends a run, column position u, coordinate cc): walks back over the run's chunks
+        auto widx = [](int q) { return (q % SUB) * 16 + ((q / SUB) & 1) * 8 + q / (2 * SUB); };
         const int per = 8 * dim;
+        if (ek == KIND_FIRST) {      // per-sender directions: one entry per (edge, direction, coordinate), no sum
+          const int pp = dim * dim;
 #pragma unroll 1
-        for (int item = sc; item < P * per; item += TC_SIDE) {
-          const int pch = item / per, rem = item - pch * per, u = rem / dim, cc = rem - u * dim;
-          auto widx = [](int q) { return (q % SUB) * 16 + ((q / SUB) & 1) * 8 + q / (2 * SUB); };
+          for (int item = sc; item < P * pp; item += TC_SIDE) {
+            const int pch = item / pp, rem = item - pch * pp, u = 1 + dim + rem / dim, cc = rem % dim;
+            const uint32_t cw = TCW(chw)[tb * 32 + widx(pch)];
+            const int ed = ch_gid(cw), i = ed / (n - 1);
+            int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
+            const int col = (pch % SUB) * 128 + ((pch / SUB) & 1) * 64 + (pch / (2 * SUB)) * 8 + u;
+            TCF(xtacc)[(i * dim + cc) * D + j * dim + (u - 1 - dim)] += cd[col * 3 + cc];
+          }
+        }
+        // one work item per (chunk that ends a run, column position u, coordinate cc): walks back over the run's chunks
+        const uint32_t runmask = (uint32_t)e.hdr(tb, TH_RUNMASK);
+        const int nruns = __popc(runmask);
+#pragma unroll 1
+        for (int item = sc; item < nruns * per; item += TC_SIDE) {
+          const int ri = item / per, rem = item - ri * per, u = rem / dim, cc = rem - u * dim;
+          const int pch = __fns(runmask, 0, ri + 1);
           auto colof = [&](int q) { return (q % SUB) * 128 + ((q / SUB) & 1) * 64 + (q / (2 * SUB)) * 8 + u; };
           const uint32_t cw = TCW(chw)[tb * 32 + widx(pch)];
           if (u >= ch_cnt(cw)) continue;
           const int ed = ch_gid(cw), i = ed / (n - 1);
-          if (ek == KIND_FIRST && u > dim) {                       // per-sender direction: one entry per edge, no sum
-            int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
-            TCF(xtacc)[(i * dim + cc) * D + j * dim + (u - 1 - dim)] += cd[colof(pch) * 3 + cc];
-            continue;
-          }
-          if (!(cw & CH_RUNEND)) continue;
+          if (ek == KIND_FIRST && u > dim) continue;
           if (u == 0 && !(cw & CH_OWNER)) continue;              // repeated primal columns
           if (ek == KIND_LAST && u > 0 && u - 1 != cc) continue;   // only the Jacobian diagonal is needed in the last block
           float acc = 0.f;
@@ -1122,17 +1136,22 @@ struct EngineTC {
         const float bav = bp.ba[0];
         float aco[2], bco[2];
         const uint32_t cw = e.my_chw(tb, lane >> 2);
+        const float raw[2] = {e.full_dot(pd, hh, sub, 2 * lane), e.full_dot(pd, hh, sub, 2 * lane + 1)};
+        float eg[2];
+        if constexpr (DIV) {      // the gate of the chunk's edge comes from its primal column = first column of lane & ~3
+          const float rawp = __shfl_sync(0xffffffffu, raw[0], lane & ~3);
+          eg[0] = eg[1] = fast_sigmoid(rawp + bav);
+        } else {
+          eg[0] = fast_sigmoid(raw[0] + bav);
+          eg[1] = fast_sigmoid(raw[1] + bav);
+        }
 #pragma unroll
         for (int u2 = 0; u2 < 2; ++u2) {
-          const int c = 2 * lane + u2, u = c & 7;
+          const int u = (2 * lane + u2) & 7;
           const bool valid = (cw & CH_VALID) && u < ch_cnt(cw);
-          const float raw = e.full_dot(pd, hh, sub, c);
-          float eg;
-          if constexpr (DIV) eg = ecnf_sigmoid(e.full_dot(pd, hh, sub, c & ~7) + bav);
-          else eg = ecnf_sigmoid(raw + bav);
           const bool prim = !DIV || u == 0;
-          aco[u2] = !valid ? 0.f : (prim ? ((!DIV || (cw & CH_OWNER)) ? eg : 0.f) : eg);
-          bco[u2] = (!valid || prim) ? 0.f : eg * (1.f - eg) * raw;
+          aco[u2] = !valid ? 0.f : (prim ? ((!DIV || (cw & CH_OWNER)) ? eg[u2] : 0.f) : eg[u2]);
+          bco[u2] = (!valid || prim) ? 0.f : eg[u2] * (1.f - eg[u2]) * raw[u2];
         }
         *reinterpret_cast<float2*>(TCF(wA) + warp * 64 + 2 * lane) = make_float2(aco[0], aco[1]);
         *reinterpret_cast<float2*>(TCF(wB) + warp * 64 + 2 * lane) = make_float2(bco[0], bco[1]);
@@ -1194,18 +1213,20 @@ struct EngineTC {
         // the window is complete: write its aggregate to global (coalesced) and clear the accumulators
         e.epi_bar();
         const int win_i = e.hdr(tb, TH_WIN_I), win_nr = e.hdr(tb, TH_WIN_NR), win_s = e.hdr(tb, TH_WIN_S), win_ns = e.hdr(tb, TH_WIN_NS);
-        const int rows = win_nr * win_ns;
         const float inv_sqrt_nb = rsqrtf((float)(e.n - 1));
         const size_t cstride = (size_t)(a.lay.mrows + 1) * U;
         float* m0p = TCF(macc) + e.fu;
         constexpr int RG = TC_EPI / U;       // row groups handled in parallel
-        for (int rr = e.tid / U; rr < rows; rr += RG) {
-          const int wi = rr / win_ns, ws = rr - wi * win_ns, i = win_i + wi;
-          const int gslot = (kind == TT_FIRST) ? (ws == 0 ? 0 : 1 + i * e.dim + (ws - 1)) : win_s + ws;
-          float sum = 0.f;
+        for (int wi = 0; wi < win_nr; ++wi) {
+          const int i = win_i + wi;
+          for (int ws = e.tid / U; ws < win_ns; ws += RG) {
+            const int rr = wi * win_ns + ws;
+            const int gslot = (kind == TT_FIRST) ? (ws == 0 ? 0 : 1 + i * e.dim + (ws - 1)) : win_s + ws;
+            float sum = 0.f;
 #pragma unroll
-          for (int cp = 0; cp < 2 * SUB; ++cp) { sum += m0p[cp * cstride + rr * U]; m0p[cp * cstride + rr * U] = 0.f; }
-          e.Mg()[((size_t)i * e.ND + gslot) * U + e.fu] = sum * inv_sqrt_nb;
+            for (int cp = 0; cp < 2 * SUB; ++cp) { sum += m0p[cp * cstride + rr * U]; m0p[cp * cstride + rr * U] = 0.f; }
+            e.Mg()[((size_t)i * e.ND + gslot) * U + e.fu] = sum * inv_sqrt_nb;
+          }
         }
         e.epi_bar();
       }
