@@ -475,7 +475,7 @@ def bench_train(c, *, steps: int = 10, cpu: bool = False):
         xd = x_host.to(c.dev, non_blocking=True)
         fd = feat_host.to(c.dev, non_blocking=True)
         st, info = flow_matching_update_fn(cnf, opt.update, st, xd, fd, grad_allreduce=hook,
-                                           global_offset=c.rank * B, loss_denominator=denom)
+                                           global_offset=c.rank * B, loss_denominator=denom, donate=True)
         if read_loss:
             loss_host.copy_(info["loss"].reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()

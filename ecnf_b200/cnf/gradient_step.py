@@ -20,10 +20,13 @@ class TrainingState(NamedTuple):
 
 def flow_matching_update_fn(cnf: FlowMatchingCNF, opt_update, state: TrainingState, x_data, features=None,
                             ema_beta: float = 0.999, *, x0=None, t=None, grad_allreduce=None, global_offset: int = 0,
-                            loss_denominator: Optional[float] = None):
+                            loss_denominator: Optional[float] = None, donate: bool = False):
     """ecnf/cnf/gradient_step.py:20-53.  `opt_update` must be the bound `update` of ecnf_b200.utils.optim.Adam
     (the stand-in for optax.adam(...).update).  Returns (new_state, info) with info = {loss, grad_norm,
-    update_norm} as 0-d device tensors.  `grad_allreduce(flat_grad, loss)` is the data-parallel hook."""
+    update_norm} as 0-d device tensors.  `grad_allreduce(flat_grad, loss)` is the data-parallel hook.
+    `donate=True` is jax's donate_argnums for the state: parameters, moments and EMA are updated in place and the returned
+    state aliases the buffers of the one passed in (which must not be used again); the default copies them, as a jitted
+    function without donation returns fresh buffers."""
     opt = getattr(opt_update, "__self__", None)
     if not isinstance(opt, Adam):
         raise TypeError("opt_update must be ecnf_b200.utils.optim.Adam(...).update")
@@ -36,10 +39,16 @@ def flow_matching_update_fn(cnf: FlowMatchingCNF, opt_update, state: TrainingSta
     if grad_allreduce is not None:
         loss = grad_allreduce(grad, loss)
     ost: AdamState = state.opt_state
-    new_flat = packed.flat.clone()
-    mu, nu = ost.mu.clone(), ost.nu.clone()
     ema_on = isinstance(state.ema_params, (PackedParams, dict))
-    ema = eng.pack(state.ema_params).flat.clone() if ema_on else None
+    if donate:
+        new_flat, mu, nu = packed.flat, ost.mu, ost.nu
+        ema = eng.pack(state.ema_params).flat if ema_on else None
+        if ema is not None and ema.data_ptr() == new_flat.data_ptr():
+            ema = ema.clone()          # the caller seeded the EMA with the parameter buffer itself
+    else:
+        new_flat = packed.flat.clone()
+        mu, nu = ost.mu.clone(), ost.nu.clone()
+        ema = eng.pack(state.ema_params).flat.clone() if ema_on else None
     lr = opt.learning_rate(ost.count)
     norms = eng.adam_step(new_flat, grad, mu, nu, ost.count, lr, ema, opt.b1, opt.b2, opt.eps, ema_beta)
     info = {"loss": loss, "grad_norm": norms[0], "update_norm": norms[1]}

@@ -291,17 +291,32 @@ __global__ void colsum_kernel(const float* __restrict__ Z, int M, int N, float* 
   }
 }
 
-__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int R, int Cc) {
+// all weight transposes of a step in ONE launch: blockIdx.y = matrix, blockIdx.x strides over its 32 x 32 tiles
+struct TrItem {
+  const float* src;
+  float* dst;
+  int R, C;
+};
+struct TrList {
+  int n;
+  TrItem it[112];
+};
+__global__ void transpose_all_kernel(const __grid_constant__ TrList list) {
   __shared__ float tile[32][33];
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = by + i, c = bx + threadIdx.x;
-    if (r < R && c < Cc) tile[i][threadIdx.x] = W[(size_t)r * Cc + c];
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = bx + i, r = by + threadIdx.x;
-    if (r < R && c < Cc) Wt[(size_t)c * R + r] = tile[threadIdx.x][i];
+  const TrItem it = list.it[blockIdx.y];
+  const int tx = (it.C + 31) / 32, ty = (it.R + 31) / 32;
+  for (int t = blockIdx.x; t < tx * ty; t += gridDim.x) {
+    const int bx = (t % tx) * 32, by = (t / tx) * 32;
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = by + i, c = bx + threadIdx.x;
+      if (r < it.R && c < it.C) tile[i][threadIdx.x] = it.src[(size_t)r * it.C + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = bx + i, r = by + threadIdx.x;
+      if (r < it.R && c < it.C) it.dst[(size_t)c * it.R + r] = tile[threadIdx.x][i];
+    }
   }
 }
 
@@ -311,12 +326,13 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
 struct Dims {
   int B, n, dim, D, E, H, U, T, L, nfeat;
   float C, sigma_min;
+  float freqs[8];   // fp32 timestep frequencies (build_cnf.py:25-27), from the model handle
 };
 
 // x_t, u_t (core.py:35-39), centring, time embedding (build_cnf.py:18-32), embedding lookup (build_cnf.py:79)
 __global__ void fm_prep_kernel(Dims d, const float* __restrict__ x_data, const float* __restrict__ x0,
                                const float* __restrict__ t, const int32_t* __restrict__ feat,
-                               const float* __restrict__ embed, const float* freqs8, float* __restrict__ ut,
+                               const float* __restrict__ embed, float* __restrict__ ut,
                                float* __restrict__ mu, float* __restrict__ xs0, float* __restrict__ tau,
                                float* __restrict__ h0) {
   const int g = blockIdx.x, tid = threadIdx.x;
@@ -337,7 +353,7 @@ __global__ void fm_prep_kernel(Dims d, const float* __restrict__ x_data, const f
   }
   if (tid >= 32 && tid < 32 + d.T / 2) {
     const int k = tid - 32;
-    const float arg = (tt * 1000.f) * freqs8[k];
+    const float arg = (tt * 1000.f) * d.freqs[k];
     tau[(size_t)g * d.T + k] = sinf(arg);
     tau[(size_t)g * d.T + k + d.T / 2] = cosf(arg);
   }
@@ -793,10 +809,11 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   Dims d;
   d.B = (int)B; d.n = c.n_frames; d.dim = c.dim; d.D = d.n * d.dim; d.E = d.n * (d.n - 1); d.H = H; d.U = U;
   d.T = c.time_dim; d.L = c.n_layers; d.nfeat = c.n_features; d.C = c.normalization_constant; d.sigma_min = c.sigma_min;
+  for (int k = 0; k < 8; ++k) d.freqs[k] = c.freqs[k];
   const int nb = c.n_blocks, L = c.n_layers, sms = m->num_sms;
   const size_t NB = (size_t)B * d.n, EB = (size_t)B * d.E;
   Arena ar{reinterpret_cast<char*>(ws), 256, 0};
-  float* freqs = ar.take(8);
+  ar.take(8);   // (was: a device copy of the frequency table)
   float* ut = ar.take(B * d.D);
   float* mu = ar.take(B * 4);
   float* tau = ar.take(B * d.T);
@@ -830,13 +847,18 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   float* Wt = ar.take((size_t)m->param_count);
   const EcnfModelDev td = ecnf_make_dev(m, Wt);  // transposed weights live at the same offsets
 
-  ECNF_CHECK_CUDA(cudaMemcpyAsync(freqs, c.freqs, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
   ECNF_CHECK_CUDA(cudaMemsetAsync(out_grad, 0, (size_t)m->param_count * sizeof(float), st));
   ECNF_CHECK_CUDA(cudaMemsetAsync(out_loss, 0, sizeof(float), st));
 
+  TrList trl;
+  trl.n = 0;
+  auto transpose_flush = [&]() {
+    if (trl.n > 0) transpose_all_kernel<<<dim3(16, trl.n), dim3(32, 8), 0, st>>>(trl);
+    trl.n = 0;
+  };
   auto transpose = [&](const float* W, const float* Wt_c, int R, int Cc) {
-    dim3 blk(32, 8), grd((Cc + 31) / 32, (R + 31) / 32);
-    transpose_kernel<<<grd, blk, 0, st>>>(W, const_cast<float*>(Wt_c), R, Cc);
+    if (trl.n == 112) transpose_flush();
+    trl.it[trl.n++] = TrItem{W, const_cast<float*>(Wt_c), R, Cc};
   };
   for (int b = 0; b < nb; ++b) {
     const EcnfBlockParams &p = md.blk[b], &q = td.blk[b];
@@ -852,6 +874,7 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
       transpose(p.Wh[L], q.Wh[L], U, H);
     }
   }
+  transpose_flush();
   ECNF_CHECK_CUDA(cudaGetLastError());
 
   auto gemm_args = [](const float* A, const float* W, float* C, int M) {
@@ -865,7 +888,7 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   int rc;
 
   // ------------------------------ forward ------------------------------
-  fm_prep_kernel<<<(unsigned)B, 128, 0, st>>>(d, x_data, x0, t, feat, md.embed, freqs, ut, mu, xs[0], tau, hprev[0]);
+  fm_prep_kernel<<<(unsigned)B, 128, 0, st>>>(d, x_data, x0, t, feat, md.embed, ut, mu, xs[0], tau, hprev[0]);
   for (int b = 0; b < nb; ++b) {
     const EcnfBlockParams& p = md.blk[b];
     const bool last = (b == nb - 1);
