@@ -41,6 +41,9 @@ using namespace ecnf_tc;
 
 constexpr int TC_NT = 384;          // 8 epilogue warps + 3 side warps + 1 MMA-issue warp (12 warps: 168 registers each)
 constexpr int TC_EPI = 256, TC_SIDE = 96;
+#ifndef TC_WPREFETCH
+#define TC_WPREFETCH 0   // 1: 2 KB of spills at 168 registers (measured: slower)
+#endif
 constexpr int TC_BOP = 65536;       // one B-operand buffer: hi image [K = 128][N = 128] + lo image
 constexpr uint32_t TC_LBO = 128, TC_SBO = 2048;       // MN-major B (activations written by the epilogue threads)
 constexpr uint32_t TC_LBO_K = 2048, TC_SBO_K = 128;   // K-major B (the gathered layer-0 operand)
@@ -242,7 +245,7 @@ __host__ __device__ inline TcSmemLayout make_tc_layout(int n, int dim, int MR) {
   L.wA = take(8 * 64 * 4);
   L.wB = take(8 * 64 * 4);
   L.cdbuf = take(SUB * 128 * 3 * 4);
-  L.egv = take(E * 3 * 4);
+  L.egv = take(E * 4 * 4);     // per edge: v = x_i - x_j (3 floats) and the packed node pair (i | j << 8)
   L.bars = take(128);
   L.prof = take(32 * 8);
   L.total_bytes = o;
@@ -438,6 +441,49 @@ struct EngineTC {
       *reinterpret_cast<uint4*>(base + 32768 + g8 * (int)TC_SBO) = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
+  // The same three steps on one 32-column half (chunks [4 hf, 4 hf + 4)) at a time, so that the TMEM load of the second half is
+  // in flight while the first half goes through the rule, the split and the stores.
+  __device__ __forceinline__ void ld_half_issue(int s, int hf, uint32_t (&x)[32]) { tmem_ld32(my_acc(s) + 32u * hf, x); }
+  template <bool L0>
+  __device__ __forceinline__ void act_half(float (&v)[64], int hf, float bias, int tb, float wdf) {
+    const float* sdp = TCF(colsd) + (tb * SUB + sub) * 128 + 64 * hh;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int ch = 4 * hf + c4;
+      if constexpr (L0) {
+        const float4 s0 = reinterpret_cast<const float4*>(sdp)[2 * ch], s1 = reinterpret_cast<const float4*>(sdp)[2 * ch + 1];
+        v[8 * ch] = fmaf(s0.x, wdf, v[8 * ch]); v[8 * ch + 1] = fmaf(s0.y, wdf, v[8 * ch + 1]);
+        v[8 * ch + 2] = fmaf(s0.z, wdf, v[8 * ch + 2]); v[8 * ch + 3] = fmaf(s0.w, wdf, v[8 * ch + 3]);
+        v[8 * ch + 4] = fmaf(s1.x, wdf, v[8 * ch + 4]); v[8 * ch + 5] = fmaf(s1.y, wdf, v[8 * ch + 5]);
+        v[8 * ch + 6] = fmaf(s1.z, wdf, v[8 * ch + 6]); v[8 * ch + 7] = fmaf(s1.w, wdf, v[8 * ch + 7]);
+      }
+      if constexpr (!DIV) {      // every column is a primal row
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float z = v[8 * ch + u] + bias;
+          v[8 * ch + u] = z * fast_sigmoid(z);
+        }
+      } else {
+        const float z = v[8 * ch] + bias;
+        const float sg = fast_sigmoid(z);
+        const float cur = sg * (1.f + z * (1.f - sg));
+        v[8 * ch] = z * sg;
+#pragma unroll
+        for (int u = 1; u < 8; ++u) v[8 * ch + u] *= cur;
+      }
+    }
+  }
+  __device__ __forceinline__ void write_half(int s, const float (&v)[64], int hf, int krow) {
+    unsigned char* base = smem_tc + a.lay.bop + s * TC_BOP + (8 * hh + 4 * hf) * (int)TC_SBO + krow * 16;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) split_pack(v[32 * hf + 8 * g8 + 2 * p], v[32 * hf + 8 * g8 + 2 * p + 1], h[p], l[p]);
+      *reinterpret_cast<uint4*>(base + g8 * (int)TC_SBO) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(base + 32768 + g8 * (int)TC_SBO) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
   // tile tables live in one buffer per (slot, tile parity):  tb = slot * 2 + ((tile >> 1) & 1)
   __device__ __forceinline__ static int tb_of(int s, int tile) { return s * 2 + ((tile >> 1) & 1); }
   __device__ __forceinline__ int hdr(int tb, int k) const { return TCI(hdr)[tb * 16 + k]; }
@@ -510,6 +556,28 @@ struct EngineTC {
     else return p4[(2 * sb) * 64] + p4[(2 * sb + 1) * 64];
   }
   // weight image (hi | lo, K x 128 lanes) -> registers -> TMEM columns [col, col + K)
+  template <int K>
+  __device__ __forceinline__ void fetch_w(int img_off, uint32_t (&wv)[2][K / 4]) {
+    constexpr int NC = K / 16;     // uint4 chunks per thread and part
+    const uint4* src = reinterpret_cast<const uint4*>(img.base + img_off);
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const uint4 q = __ldg(src + (size_t)(p * (K / 8) + hh * NC + j) * 128 + f);
+        wv[p][4 * j] = q.x; wv[p][4 * j + 1] = q.y; wv[p][4 * j + 2] = q.z; wv[p][4 * j + 3] = q.w;
+      }
+  }
+  template <int K>
+  __device__ __forceinline__ void store_w(const uint32_t (&wv)[2][K / 4], uint32_t col) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const uint32_t addr = tmem + col + lane_addr + (uint32_t)(p * (K / 2) + hh * (K / 4));
+      if constexpr (K == 128) tmem_st32(addr, wv[p]);
+      else tmem_st16(addr, wv[p]);
+    }
+    tmem_wait_st();
+  }
   template <int K>
   __device__ __forceinline__ void load_w(int img_off, uint32_t col) {
     constexpr int NC = K / 16;     // uint4 chunks per thread and part
@@ -643,8 +711,16 @@ struct EngineTC {
             // the weights two layers ahead go into the buffer that layer q's MMAs (complete once done[last slot]
             // fires) have been reading
             const bool do_w = p.stream && last_slot && q + 2 < total_q;
+#if TC_WPREFETCH
+            // fetched into registers before the wait (the L2 latency hides behind it), stored to TMEM after it
+            uint32_t wv[2][32];
+            if (do_w) fetch_w<128>(p.wimg((w + 2) % NL), wv);
+            wait_done(s);
+            if (do_w) { qbeg(); store_w<128>(wv, TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
+#else
             wait_done(s);
             if (do_w) { qbeg(); load_w<128>(p.wimg((w + 2) % NL), TC_WCOL + 128 * (q & 1)); qend(P_WLOAD); }
+#endif
             p.epi(s, tb, tile, w);
             if (w < NL - 1) arrive(B_READY, s);
             else if constexpr (P::side_build) arrive(B_HEADS, s);
@@ -897,17 +973,19 @@ struct EngineTC {
       for (int ed = e.tid; ed < e.E; ed += NTH) {
         const int i = ed / (n - 1), jj = ed - i * (n - 1);
         int j = i + 1 + jj; if (j >= n) j -= n;
-        for (int c = 0; c < 3; ++c) TCF(egv)[ed * 3 + c] = c < dim ? TCF(xs)[i * dim + c] - TCF(xs)[j * dim + c] : 0.f;
+        float vv[3];
+        for (int c = 0; c < 3; ++c) vv[c] = c < dim ? TCF(xs)[i * dim + c] - TCF(xs)[j * dim + c] : 0.f;
+        reinterpret_cast<float4*>(TCF(egv))[ed] = make_float4(vv[0], vv[1], vv[2], __int_as_float(i | (j << 8)));
       }
     }
     // (i, j) of an edge, its squared length with the safe rule (numerical.py:7-10)
-    __device__ __forceinline__ void edge_geo(int ed, int& i, int& j, float& sq) const {
+    __device__ __forceinline__ float4 edge_geo(int ed, int& i, int& j, float& sq) const {
       const KernelArgs& a = e.a;
-      const int n = e.n;
-      i = ed / (n - 1);
-      j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
-      const float v0 = TCF(egv)[ed * 3], v1 = TCF(egv)[ed * 3 + 1], v2 = TCF(egv)[ed * 3 + 2];
-      sq = fmaf(v2, v2, fmaf(v1, v1, v0 * v0));
+      const float4 g = reinterpret_cast<const float4*>(TCF(egv))[ed];
+      const int ij = __float_as_int(g.w);
+      i = ij & 255; j = ij >> 8;
+      sq = fmaf(g.z, g.z, fmaf(g.y, g.y, g.x * g.x));
+      return g;
     }
 
     // ---- side warpgroup: one thread per tile column (x SUB sub-tiles) ---------------------------------------------------
@@ -926,8 +1004,8 @@ struct EngineTC {
         const bool valid = e.col_of(cw, c, ed, q);
         int rs = n * ND, rr = n * ND;        // the all-zero row
         if (valid && (q == 0 || htan)) {
-          const int i = ed / (n - 1);
-          int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
+          const int ij = __float_as_int(TCF(egv)[ed * 4 + 3]);
+          const int i = ij & 255, j = ij >> 8;
           const int slot = q == 0 ? 0 : 1 + dirmap(ekind(), q - 1, i, j, e.dim);
           rs = j * ND + slot; rr = i * ND + slot;
         }
@@ -962,7 +1040,8 @@ struct EngineTC {
         int mr = dump;
         if (valid) {
           int i, j; float sq;
-          edge_geo(ed, i, j, sq);
+          const float4 g = edge_geo(ed, i, j, sq);
+          const float gv[3] = {g.x, g.y, g.z};
           const bool isz = (sq == 0.f);
           int gslot = 0;
           if (q == 0) {
@@ -971,8 +1050,9 @@ struct EngineTC {
             const int k = dirmap(ekind(), q - 1, i, j, dim);
             gslot = 1 + k;
             float acc = 0.f;
-            for (int cc = 0; cc < dim; ++cc)
-              acc = fmaf(TCF(egv)[ed * 3 + cc], TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k], acc);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+              if (cc < dim) acc = fmaf(gv[cc], TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k], acc);
             sd = isz ? 0.f : 2.f * acc;
           }
           if (want_msg && !((c & 7) == 0 && DIV && !(cw & CH_OWNER))) {      // a repeated primal column contributes nothing
@@ -1015,14 +1095,15 @@ struct EngineTC {
         float val[3] = {0.f, 0.f, 0.f};
         if (valid) {
           int i, j; float sq;
-          edge_geo(ed, i, j, sq);
+          const float4 g = edge_geo(ed, i, j, sq);
+          const float gv[3] = {g.x, g.y, g.z};
           const bool isz = (sq == 0.f);
           const float len = sqrtf(isz ? 1.f : sq), inv = 1.f / (e.m.C + len);
           const int h2 = c >> 6, cl = c & 63;
           if (q == 0) {
             const float pg = e.full_dot(pd, h2, sb, cl) + bpv;
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) val[cc] = pg * TCF(egv)[ed * 3 + cc] * inv;
+            for (int cc = 0; cc < 3; ++cc) val[cc] = pg * gv[cc] * inv;
           } else {
             const int k = dirmap(ek, q - 1, i, j, dim);
             const float pg = e.full_dot(pd, h2, sb, cl & ~7) + bpv, pdv = e.full_dot(pd, h2, sb, cl);
@@ -1030,7 +1111,7 @@ struct EngineTC {
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
               if (cc < dim) {
-                const float vc = TCF(egv)[ed * 3 + cc];
+                const float vc = gv[cc];
                 const float vd = TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k];
                 val[cc] = (pdv * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
               }
@@ -1065,8 +1146,8 @@ struct EngineTC {
           for (int item = sc; item < P * pp; item += TC_SIDE) {
             const int pch = item / pp, rem = item - pch * pp, u = 1 + dim + rem / dim, cc = rem % dim;
             const uint32_t cw = TCW(chw)[tb * 32 + widx(pch)];
-            const int ed = ch_gid(cw), i = ed / (n - 1);
-            int j = i + 1 + (ed - i * (n - 1)); if (j >= n) j -= n;
+            const int ij = __float_as_int(TCF(egv)[ch_gid(cw) * 4 + 3]);
+            const int i = ij & 255, j = ij >> 8;
             const int col = (pch % SUB) * 128 + ((pch / SUB) & 1) * 64 + (pch / (2 * SUB)) * 8 + u;
             TCF(xtacc)[(i * dim + cc) * D + j * dim + (u - 1 - dim)] += cd[col * 3 + cc];
           }
@@ -1081,7 +1162,7 @@ struct EngineTC {
           auto colof = [&](int q) { return (q % SUB) * 128 + ((q / SUB) & 1) * 64 + (q / (2 * SUB)) * 8 + u; };
           const uint32_t cw = TCW(chw)[tb * 32 + widx(pch)];
           if (u >= ch_cnt(cw)) continue;
-          const int ed = ch_gid(cw), i = ed / (n - 1);
+          const int i = __float_as_int(TCF(egv)[ch_gid(cw) * 4 + 3]) & 255;
           if (ek == KIND_FIRST && u > dim) continue;
           if (u == 0 && !(cw & CH_OWNER)) continue;              // repeated primal columns
           if (ek == KIND_LAST && u > 0 && u - 1 != cc) continue;   // only the Jacobian diagonal is needed in the last block
@@ -1107,13 +1188,27 @@ struct EngineTC {
       float v[64];
       e.qbeg();
       if (w == 0) e.wait_bar(B_BUILT, s);      // the side warps' per-column tables of this tile are visible to me
-      e.ld_acc(s, v);
+      const float bias = w < L ? bp.be[w][e.fu] : bp.bx[w - L][e.fu];
+      {
+        uint32_t x[32], y[32];
+        e.ld_half_issue(s, 0, x);
+        tmem_wait_ld();
+        e.ld_half_issue(s, 1, y);         // in flight while the first half is processed
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(x[c]);
+        if (w == 0) e.template act_half<true>(v, 0, bias, tb, wdf);
+        else e.template act_half<false>(v, 0, bias, tb, 0.f);
+        if (w < NL - 1) e.write_half(s, v, 0, e.f);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[32 + c] = __uint_as_float(y[c]);
+      }
       // last layer: acc[s] is drained -- the next tile of this slot (its operand may already be gathered) can start
       if (w == NL - 1 && tile + 2 < ntiles) e.arrive(B_READY, s);
-      if (w == 0) e.template act_rule<true>(v, bp.be[0][e.fu], tb, wdf);
-      else e.template act_rule<false>(v, w < L ? bp.be[w][e.fu] : bp.bx[w - L][e.fu], tb, 0.f);
+      if (w == 0) e.template act_half<true>(v, 1, bias, tb, wdf);
+      else e.template act_half<false>(v, 1, bias, tb, 0.f);
       if (w < NL - 1) {
-        e.write_B(s, v, e.f);
+        e.write_half(s, v, 1, e.f);
         e.qend(P_EPI);
         if (w == L - 1 && want_msg) { messages(s, tb, v); e.qend(P_MSG); }
       } else {
