@@ -453,13 +453,14 @@ def roofline_of(c, name: str, r: dict, div: bool):
             "traffic_source": (src + " -- a separate ncu capture of this kernel, NOT measured in this run") if src else None}
 
 
-def bench_train(c, *, steps: int = 10, cpu: bool = False):
+def bench_train(c, *, steps: int = 10, cpu: bool = False, chunk: int = 0):
     """QM9-positional FM training step (loss + grad + all-reduce + Adam/EMA), batch 512 per GPU; every step copies its
     batch from pinned host memory and reads the loss back (the e2e figure IS the figure)."""
     from ecnf_b200.cnf import flow_matching_update_fn, TrainingState
     from ecnf_b200.distributed import make_grad_allreduce
     from ecnf_b200.utils.optim import Adam, warmup_cosine_decay_schedule
     cnf, eng, params = make_model(c, "qm9", head_variance=0.001)
+    eng.set_fm_chunk(chunk)                               # graphs per chunk of the minibatch (0 = the library's choice)
     B = 512
     opt = Adam(warmup_cosine_decay_schedule(1e-4, 1e-4, 10, 100_000, 0.0))
     state = TrainingState(params=params, opt_state=opt.init(params), key=c.rank, ema_params=params)
@@ -546,6 +547,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baselines")
     ap.add_argument("--adaptive", action="store_true", help="PID-controlled steps (rtol=atol=1e-5) instead of dt=0.05")
     ap.add_argument("--sweep-max", type=int, default=1_000_000)
+    ap.add_argument("--fm-chunk", type=int, default=0, help="fm workload: graphs per chunk of the minibatch (0 = automatic)")
     ap.add_argument("--no-count", action="store_true", help="skip the profiler pass that counts kernel launches (one extra step)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -673,14 +675,14 @@ def main():
                              launches=total_launches)
 
     elif args.workload == "fm":
-        ft = bench_train(c, steps=max(args.steps, 10), cpu=not args.no_cpu)
+        ft = bench_train(c, steps=max(args.steps, 10), cpu=not args.no_cpu, chunk=args.fm_chunk)
         line = {"metric": ft["metric"], "value": ft["value"], "unit": "steps/s", "n_gpus": c.world,
                 "steps": max(args.steps, 10), "warmup": 3, "ms_per_step": ft["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "qm9pos_flow_matching_update_fn_batch512_per_gpu", "global_batch": ft["global_batch"],
                            "parallelism": f"dp{c.world} (minibatch shards, one NCCL all-reduce of the flat gradient)"},
                 "roofline": ft["roofline"], "cpu_baseline": ft.get("cpu_baseline"), "e2e": ft["e2e"],
-                "gpu_launches": ft["launches_per_step"] * max(args.steps, 10), "extra": {"loss": ft["loss"], "kernels_per_step": ft["kernels_per_step"]}}
+                "gpu_launches": ft["launches_per_step"] * max(args.steps, 10), "extra": {"loss": ft["loss"], "kernels_per_step": ft["kernels_per_step"], "fm_chunk": args.fm_chunk}}
 
     if c.rank == 0:
         def clean(o):

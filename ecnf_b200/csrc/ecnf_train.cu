@@ -776,6 +776,23 @@ struct Arena {
   }
 };
 
+// Graphs per chunk of a minibatch (ecnf_model_set_fm_chunk; 0 = automatic).  A chunk's [edge rows x U] fp32 matrices are
+// sized to stay (mostly) resident in the 126 MB L2 between the kernel that writes one and the kernel that reads it, so the
+// layer-by-layer GEMMs read their operand from L2 instead of HBM; the gradients of the chunks accumulate.
+constexpr int64_t ECNF_FM_CHUNK_BYTES = 1LL << 40;   // automatic chunking: bytes of one [edge rows x U] fp32 matrix per chunk
+int64_t fm_chunk_graphs(const ecnf_model* m, int64_t B) {
+  int64_t c = m->fm_chunk;
+  if (c <= 0) {
+    const ecnf_config& cf = m->cfg;
+    const int64_t bytes_per_graph = (int64_t)cf.n_frames * (cf.n_frames - 1) * cf.mlp_units * 4;
+    c = ECNF_FM_CHUNK_BYTES / bytes_per_graph;
+    if (c < 1) c = 1;
+    const int64_t nchunks = (B + c - 1) / c;          // equal chunks
+    c = (B + nchunks - 1) / nchunks;
+  }
+  return c < B ? c : B;
+}
+
 size_t fm_bytes(const ecnf_model* m, int64_t B) {
   const ecnf_config& c = m->cfg;
   const size_t n = c.n_frames, D = n * c.dim, E = n * (n - 1), H = c.n_hidden, U = c.mlp_units, T = c.time_dim,
@@ -800,9 +817,12 @@ size_t fm_bytes(const ecnf_model* m, int64_t B) {
   return s;
 }
 
+// One chunk of `B` graphs (rows [0, B) of the pointers given) through forward + backward.  The workspace is carved for
+// `Bws` >= B graphs; every gradient (and the loss) is ACCUMULATED, so the chunks of a minibatch add up.  `first`: clear the
+// gradient / loss and transpose the weights (once per minibatch).
 template <int U, int H>
 int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const float* t, const int32_t* feat, int64_t B,
-           float denom, float* out_loss, float* out_grad, void* ws, cudaStream_t st) {
+           int64_t Bws, bool first, float denom, float* out_loss, float* out_grad, void* ws, cudaStream_t st) {
   const ecnf_config& c = m->cfg;
   const EcnfModelDev md = ecnf_make_dev(m, m->d_params);
   const EcnfModelDev gd = ecnf_make_dev(m, out_grad);  // same layout, pointing into the gradient buffer
@@ -812,43 +832,46 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   for (int k = 0; k < 8; ++k) d.freqs[k] = c.freqs[k];
   const int nb = c.n_blocks, L = c.n_layers, sms = m->num_sms;
   const size_t NB = (size_t)B * d.n, EB = (size_t)B * d.E;
+  const size_t Bw = (size_t)Bws, NBw = Bw * d.n, EBw = Bw * d.E;   // carve-up sizes (the same for every chunk)
   Arena ar{reinterpret_cast<char*>(ws), 256, 0};
   ar.take(8);   // (was: a device copy of the frequency table)
-  float* ut = ar.take(B * d.D);
-  float* mu = ar.take(B * 4);
-  float* tau = ar.take(B * d.T);
+  float* ut = ar.take(Bw * d.D);
+  float* mu = ar.take(Bw * 4);
+  float* tau = ar.take(Bw * d.T);
   float* xs[ECNF_MAX_BLOCKS + 1];
-  for (int b = 0; b <= nb; ++b) xs[b] = ar.take(B * d.D);
-  float* dxs[2] = {ar.take(B * d.D), ar.take(B * d.D)};
-  float* cvec = ar.take(B * H);
+  for (int b = 0; b <= nb; ++b) xs[b] = ar.take(Bw * d.D);
+  float* dxs[2] = {ar.take(Bw * d.D), ar.take(Bw * d.D)};
+  float* cvec = ar.take(Bw * H);
   float* hprev[ECNF_MAX_BLOCKS + 1];
   float* hin[ECNF_MAX_BLOCKS];
-  for (int b = 0; b <= nb; ++b) hprev[b] = ar.take(NB * H);
-  for (int b = 0; b < nb; ++b) hin[b] = ar.take(NB * H);
-  float* Ps = ar.take(NB * U);
-  float* Pr = ar.take(NB * U);
+  for (int b = 0; b <= nb; ++b) hprev[b] = ar.take(NBw * H);
+  for (int b = 0; b < nb; ++b) hin[b] = ar.take(NBw * H);
+  float* Ps = ar.take(NBw * U);
+  float* Pr = ar.take(NBw * U);
   float* Mb[ECNF_MAX_BLOCKS];
   float* Zh[ECNF_MAX_BLOCKS][ECNF_MAX_LAYERS];
   float* Ze[ECNF_MAX_BLOCKS][ECNF_MAX_LAYERS];
   float* Zx[ECNF_MAX_BLOCKS][ECNF_MAX_LAYERS];
   float* pb[ECNF_MAX_BLOCKS];
   float* eb[ECNF_MAX_BLOCKS];
-  for (int b = 0; b < nb; ++b) Mb[b] = ar.take(NB * U);
+  for (int b = 0; b < nb; ++b) Mb[b] = ar.take(NBw * U);
   for (int b = 0; b < nb; ++b)
-    for (int l = 0; l < L; ++l) Zh[b][l] = ar.take(NB * U);
+    for (int l = 0; l < L; ++l) Zh[b][l] = ar.take(NBw * U);
   for (int b = 0; b < nb; ++b)
-    for (int l = 0; l < L; ++l) { Ze[b][l] = ar.take(EB * U); Zx[b][l] = ar.take(EB * U); }
-  for (int b = 0; b < nb; ++b) { pb[b] = ar.take(EB); eb[b] = ar.take(EB); }
-  float* DM = ar.take(EB * U);
-  float* dvgeo = ar.take(EB * 4);
-  float* dM = ar.take(NB * U);
-  float* dhin = ar.take(NB * H);
-  float* dh[2] = {ar.take(NB * H), ar.take(NB * H)};
+    for (int l = 0; l < L; ++l) { Ze[b][l] = ar.take(EBw * U); Zx[b][l] = ar.take(EBw * U); }
+  for (int b = 0; b < nb; ++b) { pb[b] = ar.take(EBw); eb[b] = ar.take(EBw); }
+  float* DM = ar.take(EBw * U);
+  float* dvgeo = ar.take(EBw * 4);
+  float* dM = ar.take(NBw * U);
+  float* dhin = ar.take(NBw * H);
+  float* dh[2] = {ar.take(NBw * H), ar.take(NBw * H)};
   float* Wt = ar.take((size_t)m->param_count);
   const EcnfModelDev td = ecnf_make_dev(m, Wt);  // transposed weights live at the same offsets
 
-  ECNF_CHECK_CUDA(cudaMemsetAsync(out_grad, 0, (size_t)m->param_count * sizeof(float), st));
-  ECNF_CHECK_CUDA(cudaMemsetAsync(out_loss, 0, sizeof(float), st));
+  if (first) {
+    ECNF_CHECK_CUDA(cudaMemsetAsync(out_grad, 0, (size_t)m->param_count * sizeof(float), st));
+    ECNF_CHECK_CUDA(cudaMemsetAsync(out_loss, 0, sizeof(float), st));
+  }
 
   TrList trl;
   trl.n = 0;
@@ -860,7 +883,7 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
     if (trl.n == 112) transpose_flush();
     trl.it[trl.n++] = TrItem{W, const_cast<float*>(Wt_c), R, Cc};
   };
-  for (int b = 0; b < nb; ++b) {
+  for (int b = 0; first && b < nb; ++b) {
     const EcnfBlockParams &p = md.blk[b], &q = td.blk[b];
     transpose(p.Wd, q.Wd, H, H);
     transpose(p.We[0], q.We[0], H, U);
@@ -1035,7 +1058,7 @@ extern "C" {
 
 int64_t ecnf_fm_workspace_bytes(const ecnf_model* m, int64_t B) {
   if (!m || B <= 0) return 256;
-  return (int64_t)fm_bytes(m, B);
+  return (int64_t)fm_bytes(m, fm_chunk_graphs(m, B));
 }
 
 int ecnf_fm_loss_grad(const ecnf_model* m, const float* x_data, const float* x0, const float* t, const int32_t* feat,
@@ -1057,11 +1080,28 @@ int ecnf_fm_loss_grad(const ecnf_model* m, const float* x_data, const float* x0,
   cudaStream_t st = (cudaStream_t)stream;
   t_engine = m->engine;
   const int U = m->cfg.mlp_units, H = m->cfg.n_hidden;
-  if (U == 128 && H == 64) return fm_run<128, 64>(m, x_data, x0, t, feat, B, loss_denominator, out_loss, out_grad, ws, st);
-  if (U == 256 && H == 32) return fm_run<256, 32>(m, x_data, x0, t, feat, B, loss_denominator, out_loss, out_grad, ws, st);
-  if (U == 64 && H == 32) return fm_run<64, 32>(m, x_data, x0, t, feat, B, loss_denominator, out_loss, out_grad, ws, st);
-  ecnf_set_error("unsupported (mlp_units=%d, n_hidden=%d): compiled pairs are (128,64), (256,32), (64,32)", U, H);
-  return ECNF_ERR_UNSUPPORTED;
+  if (!((U == 128 && H == 64) || (U == 256 && H == 32) || (U == 64 && H == 32))) {
+    ecnf_set_error("unsupported (mlp_units=%d, n_hidden=%d): compiled pairs are (128,64), (256,32), (64,32)", U, H);
+    return ECNF_ERR_UNSUPPORTED;
+  }
+  const int64_t Bc = fm_chunk_graphs(m, B), D = (int64_t)m->cfg.n_frames * m->cfg.dim, n = m->cfg.n_frames;
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t bn = B - b0 < Bc ? B - b0 : Bc;
+    const float *xd = x_data + b0 * D, *xz = x0 + b0 * D, *tt = t + b0;
+    const int32_t* ft = feat + b0 * n;
+    int rc;
+    if (U == 128) rc = fm_run<128, 64>(m, xd, xz, tt, ft, bn, Bc, b0 == 0, loss_denominator, out_loss, out_grad, ws, st);
+    else if (U == 256) rc = fm_run<256, 32>(m, xd, xz, tt, ft, bn, Bc, b0 == 0, loss_denominator, out_loss, out_grad, ws, st);
+    else rc = fm_run<64, 32>(m, xd, xz, tt, ft, bn, Bc, b0 == 0, loss_denominator, out_loss, out_grad, ws, st);
+    if (rc != ECNF_OK) return rc;
+  }
+  return ECNF_OK;
+}
+
+int ecnf_model_set_fm_chunk(ecnf_model* m, int64_t graphs) {
+  if (!m || graphs < 0) { ecnf_set_error("ecnf_model_set_fm_chunk: bad argument"); return ECNF_ERR_INVALID; }
+  m->fm_chunk = graphs;
+  return ECNF_OK;
 }
 
 }  // extern "C"

@@ -198,6 +198,10 @@ class Engine:
         """0 = tensor cores where the shape is eligible (default), 1 = fp32 SIMT everywhere.  Per model handle."""
         L.check(self.lib.ecnf_model_set_engine(self.handle, int(engine)), "ecnf_model_set_engine")
 
+    def set_fm_chunk(self, graphs: int) -> None:
+        """Graphs per chunk of a training minibatch (gradients accumulate over the chunks); 0 = automatic."""
+        L.check(self.lib.ecnf_model_set_fm_chunk(self.handle, int(graphs)), "ecnf_model_set_fm_chunk")
+
     @staticmethod
     def check_status(stats: torch.Tensor, what: str) -> None:
         """diffrax raises when max_steps is reached (throw=True); the kernel flags the trajectory instead.  This is the

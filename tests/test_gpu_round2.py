@@ -173,3 +173,31 @@ def test_wrappers_raise_when_max_steps_is_reached(cuda_device):
     x1 = sample_cnf(cnf, tree, 3, n_samples=4)
     x1b, lq = sample_and_log_prob_cnf(cnf, tree, 3, n_samples=4, check_status=False)
     assert torch.isfinite(x1).all() and torch.isfinite(lq).all()
+
+
+def test_fm_chunked_minibatch_accumulates_to_the_same_gradient(cuda_device):
+    """ecnf_model_set_fm_chunk: a minibatch processed in chunks (uneven last chunk) gives the loss and gradient of the
+    single pass (a different summation order only) and of fp64 autograd."""
+    n, dim, blocks, units, H, nfeat = CASES["lj13"]
+    ocfg, flat, tree, ecfg = make_pair(n, dim, blocks, units, H, n_features=nfeat)
+    eng = Engine(ecfg)
+    B = 23
+    rng = np.random.default_rng(29)
+    D = n * dim
+    x_data = O.remove_mean(torch.tensor(rng.standard_normal((B, D))), n, dim).float()
+    x0 = O.base_sample_from_noise(ocfg, torch.tensor(rng.standard_normal((B, D)))).float()
+    t = torch.tensor(rng.uniform(0, 1, B)).float()
+    feat = torch.zeros(B, n, dtype=torch.int32)
+    loss_ref, g_ref = O.fm_loss_and_grad(flat, ocfg, x_data, x0, t, feat.long(), dtype=torch.float64)
+    eng.set_fm_chunk(B)
+    loss1, grad1 = eng.fm_loss_grad(tree, x_data, x0, t, feat)
+    loss1, grad1 = loss1.clone(), grad1.clone()
+    for chunk in (5, 1, 0):
+        eng.set_fm_chunk(chunk)
+        loss, grad = eng.fm_loss_grad(tree, x_data, x0, t, feat)
+        assert abs(float(loss[0]) - float(loss1[0])) < 1e-5 * abs(float(loss1[0])), chunk
+        assert float((grad - grad1).abs().max()) < 2e-5 * float(grad1.abs().max()), chunk
+        assert abs(float(loss[0]) - float(loss_ref)) < 1e-5 * abs(float(loss_ref))
+    g = eng.unpack(grad, to_numpy=True)["params"]["EGNN_0"]["1"]["phi_e"]["Dense_1"]["kernel"]
+    gr = g_ref["EGNN_0/1/phi_e/Dense_1/kernel"].numpy()
+    assert np.abs(g - gr).max() < 1e-4 * np.abs(gr).max()
