@@ -594,6 +594,23 @@ def main():
             extra["sample_only"] = {"metric": f"LJ13 sample_cnf samples/s (no divergence, Dopri5 {fixed_tag})", "value": rs["value"],
                                     "unit": UNIT, "batch_per_gpu": 4736, "e2e": rs["e2e"], "roofline": roofline_of(c, "lj13", rs, False)}
             extra["fm_train"] = bench_train(c, cpu=not args.no_cpu)
+            if c.world > 1:
+                # strong scaling: BASELINE configs[1]'s global batch of 10 000 split over the ranks
+                b0, b1 = shard(c, 10_000)
+                rt = bench_solve(c, "lj13", b0, b1, div=True, adaptive=False, steps=2, warmup=1, target=L.TARGET_LJ, count=False)
+                extra["lj13_strong_10k"] = {"metric": METRIC + ", global batch 10 000 split over the ranks", "value": rt["value"],
+                                            "unit": UNIT, "ms_per_step": rt["ms_per_step"], "scaling": "strong",
+                                            "batch_this_rank": rt["batch_this_rank"], "roofline": roofline_of(c, "lj13", rt, True)}
+            if c.world >= 8:
+                # BASELINE configs[3]: ALDP, 100 000 trajectories sharded over the 8 GPUs, log-weights + merged ESS
+                b0, b1 = shard(c, 100_000)
+                rA = bench_solve(c, "aldp", b0, b1, div=True, adaptive=False, steps=1, warmup=1, target=L.TARGET_LJ,
+                                 e2e_steps=1, count=False)
+                extra["aldp_100k_strong"] = {"metric": "ALDP samples/s with exact log-q, 100 000 trajectories over the ranks + stand-in LJ log-weights + merged ESS",
+                                             "value": rA["value"], "unit": UNIT, "ms_per_step": rA["ms_per_step"], "scaling": "strong",
+                                             "global_batch": rA["global_batch"], "batch_this_rank": rA["batch_this_rank"],
+                                             "e2e": rA["e2e"], "reverse_ess": rA.get("reverse_ess"), "forward_ess": rA.get("forward_ess"),
+                                             "status_failures": rA["status_failures"], "roofline": roofline_of(c, "aldp", rA, True)}
             launches += extra["fm_train"].pop("launches_per_step") * 10
         cpu = None
         if c.rank == 0 and c.world == 1 and not args.no_cpu:

@@ -48,7 +48,7 @@ int run(const ecnf_model* m, int mode, const float* x, const float* t, const int
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool div = mode_div(mode);
-  const bool tc = use_tc(m, div) && !eps;   // Hutchinson probes run on the SIMT engine
+  const bool tc = use_tc(m, div);           // (Hutchinson probes: the tensor-core engine carries one tangent direction)
   const int grid = grid_for(m, B);
   KernelArgs a;
   a.m = ecnf_make_dev(m, m->d_params);

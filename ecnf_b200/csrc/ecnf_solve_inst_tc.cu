@@ -52,12 +52,13 @@ int64_t walk_images(const ecnf_model* mdl, TcImages* img, TcPrepList* list) {
 }
 
 // tile counts / offsets of the table kinds
-TcTabs make_tabs(const ecnf_model* mdl, int MR) {
+TcTabs make_tabs(const ecnf_model* mdl, int MR, int ntan = 0) {   // ntan: 0 = n * dim (exact trace), 1 = Hutchinson
+  if (ntan <= 0) ntan = mdl->cfg.n_frames * mdl->cfg.dim;
   TcTabs t{};
   int off = 0;
   for (int k = 0; k < TT_COUNT; ++k) {
     t.off[k] = off;
-    t.cnt[k] = tc_pack(k, mdl->cfg.n_frames, mdl->cfg.dim, sub_of(mdl->cfg), MR, nullptr);
+    t.cnt[k] = tc_pack(k, mdl->cfg.n_frames, mdl->cfg.dim, sub_of(mdl->cfg), MR, nullptr, ntan);
     off += t.cnt[k];
   }
   return t;
@@ -101,9 +102,9 @@ int64_t tc_flops_per_eval(const ecnf_model* mdl) {
   const int MR = pick_mrows(c, true), SUB = sub_of(c);
   int64_t sumN[TT_COUNT];
   for (int k = 0; k < TT_COUNT; ++k) {
-    const int cnt = tc_pack(k, c.n_frames, c.dim, SUB, MR, nullptr);
+    const int cnt = tc_pack(k, c.n_frames, c.dim, SUB, MR, nullptr, c.n_frames * c.dim);
     std::vector<uint32_t> buf((size_t)cnt * TC_TILE_WORDS);
-    tc_pack(k, c.n_frames, c.dim, SUB, MR, buf.data());
+    tc_pack(k, c.n_frames, c.dim, SUB, MR, buf.data(), c.n_frames * c.dim);
     sumN[k] = 0;
     for (int t = 0; t < cnt; ++t) sumN[k] += buf[(size_t)t * TC_TILE_WORDS + 32 + TH_N];
   }
@@ -119,11 +120,14 @@ int64_t tc_flops_per_eval(const ecnf_model* mdl) {
 }
 
 int tc_tile_table(const ecnf_model* mdl, int kind, uint32_t* out, int64_t cap_words) {
+  const bool hutch = kind >= 8;      // kind + 8: the one-tangent (Hutchinson) variant of the table
+  if (hutch) kind -= 8;
   if (kind < 0 || kind >= TT_COUNT) return 0;
   const ecnf_config& c = mdl->cfg;
   const int MR = pick_mrows(c, kind != TT_NODE1 && kind != TT_EDGE1);
-  const int cnt = tc_pack(kind, c.n_frames, c.dim, sub_of(c), MR, nullptr);
-  if (out && (int64_t)cnt * TC_TILE_WORDS <= cap_words) tc_pack(kind, c.n_frames, c.dim, sub_of(c), MR, out);
+  const int ntan = hutch ? 1 : c.n_frames * c.dim;
+  const int cnt = tc_pack(kind, c.n_frames, c.dim, sub_of(c), MR, nullptr, ntan);
+  if (out && (int64_t)cnt * TC_TILE_WORDS <= cap_words) tc_pack(kind, c.n_frames, c.dim, sub_of(c), MR, out, ntan);
   return cnt;
 }
 
@@ -140,10 +144,12 @@ int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, bo
   tc_prep_kernel<<<pgrid, 256, 0, st>>>(mdl->d_params, reinterpret_cast<unsigned char*>(image_ws), local);
   ECNF_CHECK_CUDA(cudaGetLastError());
   const int MR = pick_mrows(c, div);
-  a.tabs = make_tabs(mdl, MR);
+  // Hutchinson (a.eps given): one tangent direction -- the tables of kinds TT_NODE / TT_MID with two rows per group
+  const int ntan = (div && a.eps) ? 1 : c.n_frames * c.dim;
+  a.tabs = make_tabs(mdl, MR, ntan);
   uint32_t* tab_ws = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(image_ws) + images_bytes(mdl));
   a.tabs.base = tab_ws;
-  tc_tables_kernel<<<1, 32, 0, st>>>(tab_ws, c.n_frames, c.dim, sub_of(c), MR, a.tabs);
+  tc_tables_kernel<<<1, 32, 0, st>>>(tab_ws, c.n_frames, c.dim, sub_of(c), MR, ntan, a.tabs);
   ECNF_CHECK_CUDA(cudaGetLastError());
   a.lay = layout_of(c, MR);
   const size_t smem = (size_t)a.lay.total_bytes;

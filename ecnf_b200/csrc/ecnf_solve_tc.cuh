@@ -65,8 +65,9 @@ __device__ __forceinline__ float fast_sigmoid(float z) {
   return r;
 }
 
-__host__ __device__ inline int tc_rows_of_kind(int kind, int n, int dim) {
-  const int ND = 1 + n * dim;
+// ntan = tangent directions carried: n * dim (exact trace: the basis) or 1 (Hutchinson: the probe; tables TT_NODE and TT_MID)
+__host__ __device__ inline int tc_rows_of_kind(int kind, int n, int dim, int ntan) {
+  const int ND = 1 + ntan;
   return (kind == TT_NODE1 || kind == TT_EDGE1) ? 1 : kind == TT_NODE ? ND : kind == TT_FIRST ? 1 + 2 * dim : kind == TT_MID ? ND : 1 + dim;
 }
 
@@ -74,11 +75,11 @@ __host__ __device__ inline int tc_rows_of_kind(int kind, int n, int dim) {
 // when out != null.  Chunk p of a tile sits in sub-tile p % SUB, column half (p / SUB) % 2, chunk position p / (2 SUB)
 // (both halves and both sub-tiles fill evenly).  MR = rows of the message accumulator: tiles of the message-passing kinds
 // never span two windows (a window = some receivers x a slot range whose aggregate fits MR rows).
-__host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR, uint32_t* out) {
-  const int D = n * dim, ND = 1 + D, nb = n - 1;
+__host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR, uint32_t* out, int ntan) {
+  const int ND = 1 + ntan, nb = n - 1;
   const bool edge = kind >= TT_FIRST;
   const int ngroups = edge ? n * nb : n;
-  const int r = tc_rows_of_kind(kind, n, dim);
+  const int r = tc_rows_of_kind(kind, n, dim, ntan);
   const bool dense = (r == 1);
   const int CAP = 16 * SUB;
   int tile = 0, p = 0;
@@ -282,7 +283,9 @@ struct EngineTC {
   const KernelArgs& a;     // the __grid_constant__ kernel parameter
   const EcnfModelDev& m;
   const TcImages& img;
-  const int n, dim, D, ND, E;
+  const bool hutch;        // Hutchinson estimate: ONE tangent direction (the probe eps), every block of kind TT_MID
+  const int n, dim, D, ntan, ND, E;
+  const float* eps_g;      // probe of the current trajectory (global, D floats)
   const int tid, f, hh, warp, lane, sub, fu;
   const bool is_epi, is_side;
   uint32_t tmem;         // TMEM base address
@@ -306,7 +309,7 @@ struct EngineTC {
   __device__ __forceinline__ void qend(int) {}
 #endif
 
-  __device__ __forceinline__ void set_eps(const float*) {}   // Hutchinson probes run on the SIMT engine
+  __device__ __forceinline__ void set_eps(const float* e) { eps_g = e; }
   __device__ __forceinline__ float* ode_ptr() const { return TCF(ode); }
   __device__ __forceinline__ float* red_ptr() const { return TCF(red); }
   __device__ __forceinline__ uint64_t* bar(int kind, int s) const { return reinterpret_cast<uint64_t*>(smem_tc + a.lay.bars) + kind * 2 + s; }
@@ -320,8 +323,9 @@ struct EngineTC {
   __device__ __forceinline__ unsigned char* Himg() const { return reinterpret_cast<unsigned char*>(Ph() + (size_t)n * ND * U); }
 
   __device__ __forceinline__ EngineTC(const KernelArgs& a_)
-      : a(a_), m(a_.m), img(a_.img), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim), ND(DIV ? 1 + a_.m.n * a_.m.dim : 1),
-        E(a_.m.n * (a_.m.n - 1)), tid(threadIdx.x), f(threadIdx.x & 127), hh((threadIdx.x >> 7) & 1), warp(threadIdx.x >> 5),
+      : a(a_), m(a_.m), img(a_.img), hutch(DIV && a_.eps != nullptr), n(a_.m.n), dim(a_.m.dim), D(a_.m.n * a_.m.dim),
+        ntan(DIV ? (a_.eps != nullptr ? 1 : a_.m.n * a_.m.dim) : 0), ND(1 + (DIV ? (a_.eps != nullptr ? 1 : a_.m.n * a_.m.dim) : 0)),
+        E(a_.m.n * (a_.m.n - 1)), eps_g(nullptr), tid(threadIdx.x), f(threadIdx.x & 127), hh((threadIdx.x >> 7) & 1), warp(threadIdx.x >> 5),
         lane(threadIdx.x & 31), sub((threadIdx.x & 127) / U_), fu((threadIdx.x & 127) % U_), is_epi(threadIdx.x < TC_EPI),
         is_side(threadIdx.x >= TC_EPI && threadIdx.x < TC_EPI + TC_SIDE) {
     if (tid == 0) {
@@ -966,7 +970,7 @@ struct EngineTC {
       }
       for (int i = e.tid; i < D; i += NTH) { TCF(xacc)[i] = 0.f; TCF(dacc)[i] = 0.f; }
       if (DIV && kind != TT_LAST)
-        for (int i = e.tid; i < D * D; i += NTH) TCF(xtacc)[i] = 0.f;
+        for (int i = e.tid; i < D * e.ntan; i += NTH) TCF(xtacc)[i] = 0.f;
       if (want_msg)
         for (int i = e.tid; i < 2 * SUB * (a.lay.mrows + 1) * U; i += NTH) TCF(macc)[i] = 0.f;
       // per-edge geometry (egnn.py:73)
@@ -1052,7 +1056,7 @@ struct EngineTC {
             float acc = 0.f;
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc)
-              if (cc < dim) acc = fmaf(gv[cc], TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k], acc);
+              if (cc < dim) acc = fmaf(gv[cc], TCF(xt)[(i * dim + cc) * e.ntan + k] - TCF(xt)[(j * dim + cc) * e.ntan + k], acc);
             sd = isz ? 0.f : 2.f * acc;
           }
           if (want_msg && !((c & 7) == 0 && DIV && !(cw & CH_OWNER))) {      // a repeated primal column contributes nothing
@@ -1112,7 +1116,7 @@ struct EngineTC {
             for (int cc = 0; cc < 3; ++cc) {
               if (cc < dim) {
                 const float vc = gv[cc];
-                const float vd = TCF(xt)[(i * dim + cc) * D + k] - TCF(xt)[(j * dim + cc) * D + k];
+                const float vd = TCF(xt)[(i * dim + cc) * e.ntan + k] - TCF(xt)[(j * dim + cc) * e.ntan + k];
                 val[cc] = (pdv * vc + pg * vd) * inv - pg * vc * ld * inv * inv;
               }
             }
@@ -1174,7 +1178,7 @@ struct EngineTC {
           } while (q >= 0 && !(TCW(chw)[tb * 32 + widx(q)] & CH_RUNEND));
           if (u == 0) TCF(xacc)[i * dim + cc] += acc;
           else if (ek == KIND_LAST) TCF(dacc)[i * dim + cc] += acc;
-          else TCF(xtacc)[(i * dim + cc) * D + (ek == KIND_MID ? ch_qb(cw) + u - 2 : i * dim + (u - 1))] += acc;
+          else TCF(xtacc)[(i * dim + cc) * e.ntan + (ek == KIND_MID ? ch_qb(cw) + u - 2 : i * dim + (u - 1))] += acc;
         }
       }
       e.side_bar();      // cdbuf is rewritten by the next tile
@@ -1349,11 +1353,21 @@ struct EngineTC {
         TCF(xs0)[i] = v;
       }
       const float invn = 1.f / (float)n;
-      if constexpr (DIV)
-      for (int idx = tid; idx < D * D; idx += TC_EPI) {
-        const int ra = idx / D, k = idx - ra * D;
-        const int ia = ra / dim, ca = ra - ia * dim, ik = k / dim, ck = k - ik * dim;
-        TCF(xt)[idx] = (ca == ck) ? ((ia == ik ? 1.f : 0.f) - invn) : 0.f;
+      if constexpr (DIV) {
+        if (hutch) {
+          // tangent of the centred positions in the probe direction: eps - mean_nodes(eps)
+          for (int i = tid; i < D; i += TC_EPI) {
+            float mean = 0.f;
+            for (int node = 0; node < n; ++node) mean += eps_g[node * dim + i % dim];
+            TCF(xt)[i] = eps_g[i] - mean * invn;
+          }
+        } else {
+          for (int idx = tid; idx < D * D; idx += TC_EPI) {
+            const int ra = idx / D, k = idx - ra * D;
+            const int ia = ra / dim, ca = ra - ia * dim, ik = k / dim, ck = k - ik * dim;
+            TCF(xt)[idx] = (ca == ck) ? ((ia == ik ? 1.f : 0.f) - invn) : 0.f;
+          }
+        }
       }
       float* h0 = hA();
       for (int idx = tid; idx < n * H; idx += TC_EPI) {
@@ -1368,7 +1382,7 @@ struct EngineTC {
     for (int b = 0; b < m.nblocks; ++b) {
       const bool last = (b == m.nblocks - 1);
       const bool htan = DIV && b > 0;
-      const int ekind = !DIV ? TT_EDGE1 : last ? TT_LAST : (b == 0 ? TT_FIRST : TT_MID);
+      const int ekind = !DIV ? TT_EDGE1 : hutch ? TT_MID : last ? TT_LAST : (b == 0 ? TT_FIRST : TT_MID);
       const int nkind = DIV ? TT_NODE : TT_NODE1;
       pbeg();
       if (!is_side) {
@@ -1392,8 +1406,8 @@ struct EngineTC {
         epi_bar();
         const float invnb = 1.f / (float)(n - 1);
         for (int i = tid; i < D; i += TC_EPI) TCF(xs)[i] += TCF(xacc)[i] * invnb;
-        if (DIV && !last)
-          for (int i = tid; i < D * D; i += TC_EPI) TCF(xt)[i] += TCF(xtacc)[i] * invnb;
+        if (DIV && (!last || hutch))
+          for (int i = tid; i < D * ntan; i += TC_EPI) TCF(xt)[i] += TCF(xtacc)[i] * invnb;
       }
       if (is_epi || is_side) phase_bar();
       pend(P_NODE_POST);
@@ -1402,10 +1416,16 @@ struct EngineTC {
       const float fs = m.final_scaling[0];
       for (int i = tid; i < D; i += TC_EPI) fout[i] = (TCF(xs)[i] - TCF(xs0)[i] - TCF(mu)[i % dim]) * fs;
       if (DIV && tid == 0) {
-        const float invnb = 1.f / (float)(n - 1);
         float s = 0.f;
-        for (int d = 0; d < D; ++d) s += TCF(xt)[d * D + d] + TCF(dacc)[d] * invnb;
-        fout[D] = fs * (s - (float)D);
+        if (hutch) {
+          // eps . (J eps): the output tangent is fs (x_L-dot - x0-dot - mean(eps)) = fs (xt - eps)   (egnn.py:183-188)
+          for (int d = 0; d < D; ++d) s = fmaf(eps_g[d], TCF(xt)[d] - eps_g[d], s);
+          fout[D] = fs * s;
+        } else {
+          const float invnb = 1.f / (float)(n - 1);
+          for (int d = 0; d < D; ++d) s += TCF(xt)[d * D + d] + TCF(dacc)[d] * invnb;
+          fout[D] = fs * (s - (float)D);
+        }
       }
     }
     __syncthreads();
@@ -1457,9 +1477,9 @@ __global__ void tc_prep_kernel(const float* __restrict__ params, unsigned char* 
   }
 }
 
-__global__ void tc_tables_kernel(uint32_t* __restrict__ out, int n, int dim, int SUB, int MR, TcTabs tabs) {
+__global__ void tc_tables_kernel(uint32_t* __restrict__ out, int n, int dim, int SUB, int MR, int ntan, TcTabs tabs) {
   const int k = threadIdx.x;
-  if (k < TT_COUNT) tc_pack(k, n, dim, SUB, MR, out + (size_t)tabs.off[k] * TC_TILE_WORDS);
+  if (k < TT_COUNT) tc_pack(k, n, dim, SUB, MR, out + (size_t)tabs.off[k] * TC_TILE_WORDS, ntan);
 }
 
 #undef TCF

@@ -80,9 +80,11 @@ int ecnf_model_set_engine(ecnf_model* m, int engine);
  * every 128-lane x N-column tile-layer), 0 when the shape runs on the fp32 SIMT engine.  For roofline reports.   */
 int64_t ecnf_solve_tensor_flops_per_eval(const ecnf_model* m);
 /* Host copy of the tensor-core engine's tile table of one kind (0 node/primal-only, 1 node, 2 first-block edges,
- * 3 middle-block edges, 4 last-block edges): 240 uint32 per tile (128 column words: bit31 valid, bit30 primal, bit29
- * repeated primal, [0,10) group, [10,18) slot, [18,24) primal column of the segment; 64 group words; 16 header words
- * from word 192: columns per half, MMA N, first group, groups, window, flush, receivers, segment-start mask; 4 primal masks from word 224).
+ * 3 middle-block edges, 4 last-block edges, 5 edges/primal-only; kind + 8: the one-tangent (Hutchinson) variant, used for
+ * kinds 1 and 3): 48 uint32 per tile = 32 chunk words (2 sub-tiles x 16 chunks of 8 columns: bit31 valid, [0,10) group,
+ * [10,18) slot of the chunk's column 1 (0: dense chunk of 8 primal rows), [18,22) valid columns, bit22 last chunk of its
+ * thread group in a run, bit23 owner of the group's primal row, bit24 run end) + 16 header words (MMA N, flush, message
+ * window, chunks per (sub-tile, half), first/last receiver, chunk count, accumulator rows, run-end mask).
  * Returns the number of tiles (writes at most cap_words), 0 when the shape is not eligible.  Test / debug aid.      */
 int ecnf_solve_tc_tile_table(const ecnf_model* m, int kind, uint32_t* out_host, int64_t cap_words);
 

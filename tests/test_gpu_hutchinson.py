@@ -83,3 +83,27 @@ def test_probe_streams(cuda_device):
     # same trajectories (the exact path may run on the tensor-core engine: equal to rounding), another divergence estimate
     assert float((a[0] - e[0]).abs().max()) < 1e-4 * float(e[0].abs().max())
     assert not torch.equal(a[1], e[1])
+
+
+@pytest.mark.parametrize("shape", ["lj13", "aldp"])
+def test_hutchinson_tensor_core_engine_matches_simt_through_the_ode_loop(shape, cuda_device):
+    """The one-tangent (probe) mode of the tcgen05 engine against the fp32 SIMT engine, fixed-step sample + log q with
+    injected probes, on the full LJ13 net and the full ALDP net (22 atoms: several message windows per block)."""
+    n, dim, blocks, units, H, nfeat = CASES["lj13"] if shape == "lj13" else (22, 3, 3, (64, 64), 32, 22)
+    ocfg, flat, tree, ecfg = make_pair(n, dim, blocks, units, H, n_features=nfeat, head_variance=0.3)
+    eng = Engine(ecfg)
+    B = 5
+    rng = np.random.default_rng(13)
+    x0 = O.base_sample_from_noise(ocfg, torch.tensor(rng.standard_normal((B, n * dim)), dtype=torch.float32)).numpy()
+    eps = rng.standard_normal((B, n * dim)).astype(np.float32)
+    feat = np.tile(np.arange(n) % nfeat, (B, 1)).astype(np.int32)
+    ctrl = L.make_ctrl(use_fixed_step_size=True)
+    out = {}
+    for engine in (0, 1):
+        eng.set_engine(engine)
+        x1, logs, stats = eng.solve(tree, L.MODE_SAMPLE_LOGQ, x0, feat, ctrl, eps=eps)
+        out[engine] = (x1.cpu().numpy(), logs.cpu().numpy(), stats.cpu().numpy())
+    eng.set_engine(0)
+    assert (out[0][2][:, 2] == 121).all() and (out[0][2][:, 3] == 0).all()
+    assert rel_err(out[0][0], out[1][0]) < TOL
+    assert np.abs(out[0][1][:, 0] - out[1][1][:, 0]).max() < TOL * (np.abs(out[1][1][:, 0]).max() + 1)

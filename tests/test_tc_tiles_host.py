@@ -35,14 +35,16 @@ def word_index(p, sub):
 SHAPES = [(13, 3, 128, 64), (4, 2, 128, 64), (2, 2, 128, 64), (7, 3, 128, 64), (22, 3, 64, 32), (5, 3, 64, 32), (9, 2, 64, 32)]
 
 
+@pytest.mark.parametrize("hutch", [False, True])
 @pytest.mark.parametrize("n,dim,U,H", SHAPES)
-def test_tile_tables(n, dim, U, H):
+def test_tile_tables(n, dim, U, H, hutch):
+    """hutch: the one-tangent tables of the Hutchinson mode (kinds NODE and MID with two rows per group)."""
     eng = Engine(CnfConfig(n, dim, 0.01, 1.0, 3, (U,) * 2, H, 8, 1))
     SUB = 128 // U
-    D, ND, nb = n * dim, 1 + n * dim, n - 1
+    D, ND, nb = n * dim, (2 if hutch else 1 + n * dim), n - 1
     rs = {NODE1: 1, NODE: ND, FIRST: 1 + 2 * dim, MID: ND, LAST: 1 + dim, EDGE1: 1}
-    for kind in range(6):
-        tab = table(eng, kind)
+    for kind in ((NODE, MID) if hutch else range(6)):
+        tab = table(eng, kind + (8 if hutch else 0))
         assert len(tab) > 0
         r, ngroups = rs[kind], (n if kind < 2 else n * nb)
         seen, owners = set(), set()

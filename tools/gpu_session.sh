@@ -21,6 +21,11 @@ for s in "$@"; do
     prof)     for w in "lj13 148" "aldp 148" "lj13 1184 sample"; do
                 ECNF_B200_LIB=ecnf_b200/libecnf_b200_prof.so timeout 300 python tools/tc_profile.py $w >> $O/${TAG}_phase_cycles.txt 2>&1; done
               echo "== prof"; cat $O/${TAG}_phase_cycles.txt ;;
+    tests2)   timeout 900 python -m pytest tests/test_gpu_hutchinson.py tests/test_gpu_train.py tests/test_gpu_round2.py -m gpu -x -q > $O/${TAG}_tests2.log 2>&1; echo "== tests2 rc=$? $(tail -3 $O/${TAG}_tests2.log)" ;;
+    thrq)     timeout 600 python tools/throughput.py > $O/${TAG}_throughput.txt 2>&1; echo "== thr rc=$?"; cat $O/${TAG}_throughput.txt ;;
+    fmsweep)  for ch in 512 256 171 128 64; do
+                timeout 300 python bench.py --workload fm --no-cpu --fm-chunk $ch > $O/${TAG}_fm_chunk$ch.json 2> $O/${TAG}_fm_chunk$ch.err
+                echo "== fm chunk $ch rc=$? $(head -c 330 $O/${TAG}_fm_chunk$ch.json)"; done ;;
     fm)       timeout 600 python bench.py --workload fm > $O/${TAG}_fm.json 2> $O/${TAG}_fm.err; echo "== fm rc=$? $(head -c 600 $O/${TAG}_fm.json)" ;;
     aldp)     timeout 900 python bench.py --workload aldp --steps 1 --warmup 1 > $O/${TAG}_aldp.json 2> $O/${TAG}_aldp.err; echo "== aldp rc=$? $(head -c 600 $O/${TAG}_aldp.json)" ;;
     sweep)    timeout 900 python bench.py --workload sweep --steps 2 > $O/${TAG}_sweep.json 2> $O/${TAG}_sweep.err; echo "== sweep rc=$? $(head -c 900 $O/${TAG}_sweep.json)" ;;

@@ -43,3 +43,22 @@ for name, (cfg, B) in CFGS.items():
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
         print(f"{name:26s} {label:22s} B={B * rep:6d}  {ms:9.1f} ms  {B * rep / ms * 1e3:10.1f} samples/s  evals/sample {int(st[0, 2])}", flush=True)
+    if name.startswith("qm9") and "--all" not in sys.argv:
+        continue
+    # the reference's approx=True branch (Hutchinson probe, one tangent): tensor-core engine vs fp32 SIMT
+    rep = 4
+    xs = x0.repeat(rep, 1)
+    fs = None if feat is None else feat.repeat(rep, 1)
+    eps = torch.randn_like(xs)
+    for engine, label in ((0, "hutchinson (auto)"), (1, "hutchinson (fp32 SIMT)")):
+        eng.set_engine(engine)
+        eng.solve(params, L.MODE_SAMPLE_LOGQ, x0[:8], None if feat is None else feat[:8], ctrl, eps=eps[:8])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _, _, st = eng.solve(params, L.MODE_SAMPLE_LOGQ, xs, fs, ctrl, eps=eps)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        print(f"{name:26s} {label:22s} B={B * rep:6d}  {ms:9.1f} ms  {B * rep / ms * 1e3:10.1f} samples/s  evals/sample {int(st[0, 2])}", flush=True)
+    eng.set_engine(0)
