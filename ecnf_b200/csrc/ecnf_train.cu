@@ -22,6 +22,7 @@ using ecnf_tile::WCHUNK;
 // engine choice of the model handle of the ecnf_fm_loss_grad call running on this host thread (0 = tensor cores where
 // eligible, 1 = fp32 SIMT): read once at entry, so concurrent callers with different handles do not interfere
 thread_local int t_engine = 0;
+thread_local float* t_dw_partial = nullptr;   // workspace of the two-stage weight-gradient flush (set per fm_run)
 
 __device__ __forceinline__ float silu_f(float z) { return z * ecnf_sigmoid(z); }
 __device__ __forceinline__ float dsilu_f(float z) {
@@ -232,18 +233,21 @@ __global__ void __launch_bounds__(NTHREADS) dw_kernel(const float* __restrict__ 
 }
 
 __global__ void colsum_kernel(const float* __restrict__ Z, int M, int N, float* __restrict__ out, int rows_per_cta);
+// rows per CTA of colsum_kernel: >= 4 CTAs per SM for the big (edge-row) matrices, enough CTAs to cover the latency for the
+// node-row ones (9 728 rows in 38 CTAs took 27 us per launch)
+inline int colsum_rows(long long M) { return M >= 65536 ? 256 : 32; }
 
 // dW += op(A)^T dZ; bias_grad (optional) += column sums of dZ (fused into the tensor-core kernel, else a second launch)
 int launch_dw(const float* A, int lda, int a_op, const float* dZ, int ldz, float* dW, int K, int N, int M, int num_sms,
               cudaStream_t st, float* bias_grad = nullptr) {
   // the big square weight gradients (reduction over the edge rows) go to the tensor cores (ecnf_train_tc.cuh)
   if (lda == K && ldz == N && K == N && (K == 128 || K == 256) && M >= 8192 && t_engine == 0) {
-    if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
-    else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
+    if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, bias_grad, M, num_sms, st, t_dw_partial)));
+    else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, bias_grad, M, num_sms, st, t_dw_partial)));
     return ECNF_OK;
   }
   if (bias_grad) {
-    const int rows = 256;
+    const int rows = colsum_rows(M);
     colsum_kernel<<<(unsigned)((M + rows - 1) / rows), NTHREADS, 0, st>>>(dZ, M, N, bias_grad, rows);
   }
   // block shape: 128 where the dimension allows, else 64 / 32
@@ -814,6 +818,7 @@ size_t fm_bytes(const ecnf_model* m, int64_t B) {
   s += r(EB * U) + r(EB * 4);                           // DM, dvgeo
   s += r(NB * U) + 3 * r(NB * H);                       // dM, dhin, dh x2
   s += r((size_t)m->param_count);                       // transposed weights
+  s += r((size_t)m->num_sms * U * U);                   // partial images of the weight-gradient kernel
   return s;
 }
 
@@ -866,6 +871,7 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   float* dhin = ar.take(NBw * H);
   float* dh[2] = {ar.take(NBw * H), ar.take(NBw * H)};
   float* Wt = ar.take((size_t)m->param_count);
+  t_dw_partial = ar.take((size_t)m->num_sms * U * U);    // partial images of the tensor-core weight-gradient kernel
   const EcnfModelDev td = ecnf_make_dev(m, Wt);  // transposed weights live at the same offsets
 
   if (first) {
@@ -965,7 +971,7 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   int cur = 0;        // dxs[cur] = grad wrt coordinates leaving block b
   int hcur = 0;       // dh[hcur] = grad wrt h leaving block b (valid for b < nb-1)
   auto colsum = [&](const float* Z, size_t M, int N, const float* out) {
-    const int rows = 256;     // >= 4 CTAs per SM for the big (edge-row) matrices
+    const int rows = colsum_rows((long long)M);
     colsum_kernel<<<(unsigned)((M + rows - 1) / rows), NTHREADS, 0, st>>>(Z, (int)M, N, const_cast<float*>(out), rows);
   };
   for (int b = nb - 1; b >= 0; --b) {

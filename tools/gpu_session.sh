@@ -26,6 +26,9 @@ for s in "$@"; do
     fmsweep)  for ch in 512 256 171 128 64; do
                 timeout 300 python bench.py --workload fm --no-cpu --fm-chunk $ch > $O/${TAG}_fm_chunk$ch.json 2> $O/${TAG}_fm_chunk$ch.err
                 echo "== fm chunk $ch rc=$? $(head -c 330 $O/${TAG}_fm_chunk$ch.json)"; done ;;
+    fmlaunch) for ch in 512 128; do
+                timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_fm_launches_chunk$ch.csv \
+                  python tools/train_profile.py $ch > $O/${TAG}_fm_launches_chunk$ch.log 2>&1; echo "== fmlaunch $ch rc=$?"; done ;;
     fm)       timeout 600 python bench.py --workload fm > $O/${TAG}_fm.json 2> $O/${TAG}_fm.err; echo "== fm rc=$? $(head -c 600 $O/${TAG}_fm.json)" ;;
     aldp)     timeout 900 python bench.py --workload aldp --steps 1 --warmup 1 > $O/${TAG}_aldp.json 2> $O/${TAG}_aldp.err; echo "== aldp rc=$? $(head -c 600 $O/${TAG}_aldp.json)" ;;
     sweep)    timeout 900 python bench.py --workload sweep --steps 2 > $O/${TAG}_sweep.json 2> $O/${TAG}_sweep.err; echo "== sweep rc=$? $(head -c 900 $O/${TAG}_sweep.json)" ;;
