@@ -22,7 +22,6 @@ using ecnf_tile::WCHUNK;
 // engine choice of the model handle of the ecnf_fm_loss_grad call running on this host thread (0 = tensor cores where
 // eligible, 1 = fp32 SIMT): read once at entry, so concurrent callers with different handles do not interfere
 thread_local int t_engine = 0;
-thread_local float* t_dw_partial = nullptr;   // workspace of the two-stage weight-gradient flush (set per fm_run)
 
 __device__ __forceinline__ float silu_f(float z) { return z * ecnf_sigmoid(z); }
 __device__ __forceinline__ float dsilu_f(float z) {
@@ -242,8 +241,8 @@ int launch_dw(const float* A, int lda, int a_op, const float* dZ, int ldz, float
               cudaStream_t st, float* bias_grad = nullptr) {
   // the big square weight gradients (reduction over the edge rows) go to the tensor cores (ecnf_train_tc.cuh)
   if (lda == K && ldz == N && K == N && (K == 128 || K == 256) && M >= 8192 && t_engine == 0) {
-    if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, bias_grad, M, num_sms, st, t_dw_partial)));
-    else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, bias_grad, M, num_sms, st, t_dw_partial)));
+    if (K == 256) ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<256, 256>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
+    else ECNF_CHECK_CUDA((ecnf_train_tc::launch_dw<128, 128>(A, a_op, dZ, dW, bias_grad, M, num_sms, st)));
     return ECNF_OK;
   }
   if (bias_grad) {
@@ -818,7 +817,6 @@ size_t fm_bytes(const ecnf_model* m, int64_t B) {
   s += r(EB * U) + r(EB * 4);                           // DM, dvgeo
   s += r(NB * U) + 3 * r(NB * H);                       // dM, dhin, dh x2
   s += r((size_t)m->param_count);                       // transposed weights
-  s += r((size_t)m->num_sms * U * U);                   // partial images of the weight-gradient kernel
   return s;
 }
 
@@ -871,7 +869,6 @@ int fm_run(const ecnf_model* m, const float* x_data, const float* x0, const floa
   float* dhin = ar.take(NBw * H);
   float* dh[2] = {ar.take(NBw * H), ar.take(NBw * H)};
   float* Wt = ar.take((size_t)m->param_count);
-  t_dw_partial = ar.take((size_t)m->num_sms * U * U);    // partial images of the tensor-core weight-gradient kernel
   const EcnfModelDev td = ecnf_make_dev(m, Wt);  // transposed weights live at the same offsets
 
   if (first) {

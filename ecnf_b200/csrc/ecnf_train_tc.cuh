@@ -567,7 +567,7 @@ __device__ __forceinline__ void convert_chunk(const float4 (&v)[4 * (C / 32) / (
 template <int K, int N>
 __global__ void __launch_bounds__(DW_NT + 32, 1) dw_tc_kernel(const float* __restrict__ A, int a_op, const float* __restrict__ dZ,
                                                             float* __restrict__ dW, float* __restrict__ colsum, int M,
-                                                            int rows_per_cta, float* __restrict__ partial) {
+                                                            int rows_per_cta) {
   static_assert((K == 128 || K == 256) && (N == 128 || N == 256) && (K / 128) * N <= 512, "shapes");
   constexpr int A_IMG = 32 * K * 2, B_IMG = 32 * N * 2;           // bytes of one (hi or lo) image of a 32-row chunk
   constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;
@@ -687,21 +687,12 @@ __global__ void __launch_bounds__(DW_NT + 32, 1) dw_tc_kernel(const float* __res
         const int col = ch * (N / 4) + 32 * q;
         tmem_ld32(tmem + (uint32_t)(h * N) + lane_addr + (uint32_t)col, v);
         tmem_wait_ld();
-        if (partial) {
-          // two-stage flush: my 32 values as 128 contiguous bytes of this CTA's partial image (a warp stores 4 KB contiguous);
-          // dw_reduce_kernel sums the images.  (148 CTAs adding to the SAME 256 KB with red.global serialise in the L2:
-          // measured 64 us per launch, independent of M.)
-          uint4* dst = reinterpret_cast<uint4*>(partial + (size_t)blockIdx.x * (K * N) + ((size_t)(h * (N / 128) + q) * DW_NT + tid) * 32);
+        float* dst = dW + (size_t)(128 * h + lane_k) * N + col;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-        } else {
-          float* dst = dW + (size_t)(128 * h + lane_k) * N + col;
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c4), "f"(__uint_as_float(v[4 * c4])),
-                         "f"(__uint_as_float(v[4 * c4 + 1])), "f"(__uint_as_float(v[4 * c4 + 2])), "f"(__uint_as_float(v[4 * c4 + 3]))
-                         : "memory");
-        }
+        for (int c4 = 0; c4 < 8; ++c4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c4), "f"(__uint_as_float(v[4 * c4])),
+                       "f"(__uint_as_float(v[4 * c4 + 1])), "f"(__uint_as_float(v[4 * c4 + 2])), "f"(__uint_as_float(v[4 * c4 + 3]))
+                       : "memory");
       }
     }
   }
@@ -711,39 +702,8 @@ __global__ void __launch_bounds__(DW_NT + 32, 1) dw_tc_kernel(const float* __res
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// dW += sum over the `nparts` partial images written by dw_tc_kernel (image index space: ((h N/128 + q) DW_NT + tid) 32 + j
-// <-> row 128 h + (tid & 127), column (tid >> 7) N/4 + 32 q + j).  blockIdx.y = slice of the images (one red per slice).
 template <int K, int N>
-__global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dW) {
-  const int e4 = blockIdx.x * 256 + threadIdx.x;          // float4 index, < K N / 4
-  const int S = gridDim.y;
-  const float4* p = reinterpret_cast<const float4*>(partial) + e4;
-  constexpr size_t STRIDE = (size_t)K * N / 4;
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-  int q = blockIdx.y;
-  for (; q + 3 * S < nparts; q += 4 * S) {
-    const float4 x0 = __ldcg(p + (size_t)q * STRIDE), x1 = __ldcg(p + (size_t)(q + S) * STRIDE);
-    const float4 x2 = __ldcg(p + (size_t)(q + 2 * S) * STRIDE), x3 = __ldcg(p + (size_t)(q + 3 * S) * STRIDE);
-    a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
-    a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
-    a2.x += x2.x; a2.y += x2.y; a2.z += x2.z; a2.w += x2.w;
-    a3.x += x3.x; a3.y += x3.y; a3.z += x3.z; a3.w += x3.w;
-  }
-  for (; q < nparts; q += S) {
-    const float4 x0 = __ldcg(p + (size_t)q * STRIDE);
-    a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
-  }
-  const float r0 = (a0.x + a1.x) + (a2.x + a3.x), r1 = (a0.y + a1.y) + (a2.y + a3.y);
-  const float r2 = (a0.z + a1.z) + (a2.z + a3.z), r3 = (a0.w + a1.w) + (a2.w + a3.w);
-  const int j4 = e4 & 7, tid = (e4 >> 3) % DW_NT, hq = (e4 >> 3) / DW_NT, h = hq / (N / 128), qq = hq % (N / 128);
-  float* dst = dW + (size_t)(128 * h + (tid & 127)) * N + (tid >> 7) * (N / 4) + 32 * qq + 4 * j4;
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(r0), "f"(r1), "f"(r2), "f"(r3) : "memory");
-}
-
-// partial: workspace of num_sms * K * N floats for the two-stage flush (null: every CTA adds straight to dW)
-template <int K, int N>
-cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, float* colsum, int M, int num_sms, cudaStream_t st,
-                      float* partial = nullptr) {
+cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, float* colsum, int M, int num_sms, cudaStream_t st) {
   constexpr int STAGE = 2 * (32 * K * 2) + 2 * (32 * N * 2);
   const size_t smem = (size_t)DW_NS * STAGE;
   auto kern = dw_tc_kernel<K, N>;
@@ -755,9 +715,7 @@ cudaError_t launch_dw(const float* A, int a_op, const float* dZ, float* dW, floa
   }
   int rows_per_cta = ((M + num_sms - 1) / num_sms + 31) / 32 * 32;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
-  if (grid < 8) partial = nullptr;          // a handful of CTAs: the direct adds are cheaper than a second launch
-  kern<<<grid, DW_NT + 32, smem, st>>>(A, a_op, dZ, dW, colsum, M, rows_per_cta, partial);
-  if (partial) dw_reduce_kernel<K, N><<<dim3(K * N / 1024, 4), 256, 0, st>>>(partial, grid, dW);
+  kern<<<grid, DW_NT + 32, smem, st>>>(A, a_op, dZ, dW, colsum, M, rows_per_cta);
   return cudaGetLastError();
 }
 
