@@ -690,7 +690,8 @@ def main():
                    "sample": f"128 LJ13 sample_cnf trajectories x 121 evals in {dt:.1f} s (the B = 1k point extrapolates linearly)"}
         line = contract_line(c, args, metric=f"LJ13 sample_cnf samples/s (no divergence, Dopri5 {fixed_tag}), largest batch of the sweep",
                              unit=UNIT, r=last, workload="lj13_sample_cnf_sweep (load_checkpoint_measure_sampling_time.py:101-119)",
-                             cfg_extra={"global_batch": last["global_batch"], "parallelism": par},
+                             cfg_extra={"global_batch": last["global_batch"],
+                                        "parallelism": f"dp{c.world} (independent trajectories, every global batch of the sweep split over the ranks)"},
                              roofline=roofline_of(c, "lj13", last, False), cpu=cpu, extra={"sweep": table}, scaling="strong",
                              launches=total_launches)
 

@@ -2,6 +2,7 @@
 # Multi-GPU measurement session (run on a GPU box with N GPUs):  tools/run_scaling.sh N [aldp]
 # Writes one contract line per workload to gpurun_out/r2_<workload>_n<N>.json
 N=$1; shift
+mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 [ "$N" = 1 ] && RUN="python"
 PORT=29600
@@ -19,5 +20,6 @@ for w in "$@"; do
     lj13w)  run lj13_weak --workload lj13 --steps 2 --warmup 2 --no-cpu --no-extra --no-count ;;
     sweep)  run sweep --workload sweep --steps 2 --no-cpu --no-count --sweep-max ${SWEEP_MAX:-1000000} ;;
     fm)     run fm --workload fm --no-cpu ;;
+    dflt)   run default --steps 1 --warmup 1 --no-cpu ;;
   esac
 done
