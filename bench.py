@@ -696,7 +696,7 @@ def main():
                              launches=total_launches)
 
     elif args.workload == "fm":
-        ft = bench_train(c, steps=max(args.steps, 10), cpu=not args.no_cpu, chunk=args.fm_chunk)
+        ft = bench_train(c, steps=max(args.steps, 10), cpu=not args.no_cpu, chunk=args.fm_chunk, count=not args.no_count)
         line = {"metric": ft["metric"], "value": ft["value"], "unit": "steps/s", "n_gpus": c.world,
                 "steps": max(args.steps, 10), "warmup": 3, "ms_per_step": ft["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
