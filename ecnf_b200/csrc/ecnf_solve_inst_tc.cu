@@ -149,7 +149,7 @@ int launch_tc(const ecnf_model* mdl, KernelArgs& a, int grid, void* image_ws, bo
   a.tabs = make_tabs(mdl, MR, ntan);
   uint32_t* tab_ws = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(image_ws) + images_bytes(mdl));
   a.tabs.base = tab_ws;
-  tc_tables_kernel<<<1, 32, 0, st>>>(tab_ws, c.n_frames, c.dim, sub_of(c), MR, ntan, a.tabs);
+  tc_tables_kernel<<<TT_COUNT, 32, 0, st>>>(tab_ws, c.n_frames, c.dim, sub_of(c), MR, ntan, a.tabs);
   ECNF_CHECK_CUDA(cudaGetLastError());
   a.lay = layout_of(c, MR);
   const size_t smem = (size_t)a.lay.total_bytes;

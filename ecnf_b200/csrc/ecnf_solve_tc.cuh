@@ -75,7 +75,9 @@ __host__ __device__ inline int tc_rows_of_kind(int kind, int n, int dim, int nta
 // when out != null.  Chunk p of a tile sits in sub-tile p % SUB, column half (p / SUB) % 2, chunk position p / (2 SUB)
 // (both halves and both sub-tiles fill evenly).  MR = rows of the message accumulator: tiles of the message-passing kinds
 // never span two windows (a window = some receivers x a slot range whose aggregate fits MR rows).
-__host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR, uint32_t* out, int ntan) {
+// stage: optional TC_TILE_WORDS-word scratch the current tile is assembled in (the device builder passes shared memory: the
+// packing is a chain of read-modify-writes that costs ~1 ms per launch straight on global memory); it is copied out on close.
+__host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR, uint32_t* out, int ntan, uint32_t* stage = nullptr) {
   const int ND = 1 + ntan, nb = n - 1;
   const bool edge = kind >= TT_FIRST;
   const int ngroups = edge ? n * nb : n;
@@ -85,7 +87,7 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR
   int tile = 0, p = 0;
   int win_i = 0, win_nr = 0, win_s = 0, win_ns = 0, i_first = 0, i_last = 0;
   int run_start = 0;     // first chunk (index in the tile) of the current run
-  auto tp = [&](int t) { return out + (size_t)t * TC_TILE_WORDS; };
+  auto tp = [&](int t) { return stage ? stage : out + (size_t)t * TC_TILE_WORDS; };
   auto word_index = [&](int q) { return (q % SUB) * 16 + ((q / SUB) % 2) * 8 + q / (2 * SUB); };
   // chunks [run_start, p) form a run (the chunks whose coordinate contributions are summed): mark its end (CH_RUNEND) and the
   // last chunk of every thread group (CH_GRPEND: where the epilogue threads flush their message partial sums); each_chunk:
@@ -123,6 +125,8 @@ __host__ __device__ inline int tc_pack(int kind, int n, int dim, int SUB, int MR
       for (int q = 0; q < p; ++q)
         if (tp(tile)[word_index(q)] & CH_RUNEND) rm |= 1u << q;
       h[TH_RUNMASK] = rm;
+      if (stage)
+        for (int k = 0; k < TC_TILE_WORDS; ++k) out[(size_t)tile * TC_TILE_WORDS + k] = stage[k];
     }
     ++tile;
     p = 0; run_start = 0;
@@ -1477,9 +1481,11 @@ __global__ void tc_prep_kernel(const float* __restrict__ params, unsigned char* 
   }
 }
 
+// one CTA per table kind (a single thread packs: the work is sequential), the current tile staged in shared memory
 __global__ void tc_tables_kernel(uint32_t* __restrict__ out, int n, int dim, int SUB, int MR, int ntan, TcTabs tabs) {
-  const int k = threadIdx.x;
-  if (k < TT_COUNT) tc_pack(k, n, dim, SUB, MR, out + (size_t)tabs.off[k] * TC_TILE_WORDS, ntan);
+  __shared__ uint32_t stage[TC_TILE_WORDS];
+  const int k = blockIdx.x;
+  if (threadIdx.x == 0 && k < TT_COUNT) tc_pack(k, n, dim, SUB, MR, out + (size_t)tabs.off[k] * TC_TILE_WORDS, ntan, stage);
 }
 
 #undef TCF

@@ -10,7 +10,7 @@ for s in "$@"; do
     thr)      timeout 600 python tools/throughput.py --all > $O/${TAG}_throughput.txt 2>&1; echo "== thr rc=$?"; cat $O/${TAG}_throughput.txt ;;
     bench)    timeout 1500 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "== bench rc=$? $(head -c 600 $O/${TAG}_bench.json)" ;;
     benchq)   timeout 900 python bench.py --steps 2 --warmup 3 --no-extra --no-cpu > $O/${TAG}_benchq.json 2> $O/${TAG}_benchq.err; echo "== benchq rc=$? $(head -c 400 $O/${TAG}_benchq.json)" ;;
-    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $O/${TAG}_launches.csv \
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_launches.csv \
                 python bench.py --steps 1 --warmup 3 --batch 1184 --no-cpu --no-count > $O/${TAG}_launches.log 2>&1; echo "== launches rc=$?" ;;
     ncu_lj13) timeout 600 ncu --set full --clock-control none --import-source on -k regex:ecnf_solve_tc_kernel --launch-skip 1 --launch-count 1 \
                 -o $O/${TAG}_solve_lj13 -f python tools/run_solve.py lj13 148 logq 2 > $O/${TAG}_ncu_lj13.log 2>&1; echo "== ncu_lj13 rc=$?" ;;
