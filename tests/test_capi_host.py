@@ -88,3 +88,24 @@ def test_keys_shards_and_ess_merge():
     merged = merge_ess_stats_list(torch.tensor([stats(lw[:1000]), stats(lw[1000:1500]), stats(lw[1500:])], dtype=torch.float64))
     rv, fw = ess_from_stats(merged.tolist(), lw.size)
     assert abs(rv - O.reverse_ess(lw)) < 1e-10 and abs(fw - O.forward_ess(lw, np.ones(lw.size, bool))) < 1e-10
+
+
+def test_per_handle_attributes_fm_chunk_and_engine():
+    """ecnf_model_set_fm_chunk / ecnf_model_set_engine are attributes of ONE handle: the training workspace follows the
+    chunk size (a chunk's activations only), bad values are refused, and a second handle is untouched."""
+    lib = L.load()
+    qm9 = CnfConfig(19, 3, 1e-6, 2.0, 5, (256,) * 4, 32, 8, 1)
+    a, b = Engine(qm9), Engine(qm9)
+    full = lib.ecnf_fm_workspace_bytes(a.handle, 512)
+    assert full > 7e9                                    # 2 x 5 x 4 [175 104 x 256] fp32 pre-activations (7.2 GB) and more
+    a.set_fm_chunk(128)
+    quarter = lib.ecnf_fm_workspace_bytes(a.handle, 512)
+    assert quarter < 0.3 * full
+    assert lib.ecnf_fm_workspace_bytes(a.handle, 100) == lib.ecnf_fm_workspace_bytes(b.handle, 100)   # B <= chunk: one chunk
+    assert lib.ecnf_fm_workspace_bytes(b.handle, 512) == full
+    a.set_fm_chunk(0)
+    assert lib.ecnf_fm_workspace_bytes(a.handle, 512) == full
+    assert lib.ecnf_model_set_fm_chunk(a.handle, -1) == -1 and b"fm_chunk" in lib.ecnf_last_error()
+    assert lib.ecnf_model_set_engine(a.handle, 7) == -1
+    with pytest.raises(L.EcnfError):
+        a.set_engine(2)
