@@ -1,6 +1,6 @@
 #!/bin/bash
 # One-GPU measurement session (run on the GPU box through gpurun):  tools/gpu_session.sh <tag> [steps...]
-# Every step writes into gpurun_out/<tag>_*; steps: tests thr bench launches ncu_lj13 ncu_aldp ncu_sample prof fm
+# Every step writes into gpurun_out/<tag>_*; steps: tests tests2 thr thrq bench benchq launches ncu_lj13 ncu_aldp ncu_sample prof fm fmsweep fmlaunch aldp sweep
 TAG=$1; shift
 O=gpurun_out
 mkdir -p $O
@@ -29,8 +29,6 @@ for s in "$@"; do
     fmlaunch) for ch in 512 128; do
                 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_fm_launches_chunk$ch.csv \
                   python tools/train_profile.py $ch > $O/${TAG}_fm_launches_chunk$ch.log 2>&1; echo "== fmlaunch $ch rc=$?"; done ;;
-    fmab)     for rep in 1 2; do for lib in libecnf_b200.so libecnf_b200_exp.so; do
-                ECNF_B200_LIB=ecnf_b200/$lib timeout 300 python bench.py --workload fm --no-cpu --no-count 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('== fmab $lib', d['value'], d['ms_per_step'])" | tee -a $O/${TAG}_fmab.txt; done; done ;;
     fm)       timeout 600 python bench.py --workload fm > $O/${TAG}_fm.json 2> $O/${TAG}_fm.err; echo "== fm rc=$? $(head -c 600 $O/${TAG}_fm.json)" ;;
     aldp)     timeout 900 python bench.py --workload aldp --steps 1 --warmup 1 > $O/${TAG}_aldp.json 2> $O/${TAG}_aldp.err; echo "== aldp rc=$? $(head -c 600 $O/${TAG}_aldp.json)" ;;
     sweep)    timeout 900 python bench.py --workload sweep --steps 2 > $O/${TAG}_sweep.json 2> $O/${TAG}_sweep.err; echo "== sweep rc=$? $(head -c 900 $O/${TAG}_sweep.json)" ;;
