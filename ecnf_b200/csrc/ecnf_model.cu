@@ -134,6 +134,14 @@ int ecnf_model_create(const ecnf_config* cfg, const float* d_params, ecnf_model*
 
 void ecnf_model_destroy(ecnf_model* m) { delete m; }
 
+int ecnf_model_clone(const ecnf_model* m, const float* d_params, ecnf_model** out) {
+  if (!m || !out) { ecnf_set_error("ecnf_model_clone: null argument"); return ECNF_ERR_INVALID; }
+  ecnf_model* c = new ecnf_model(*m);     // config, layout, engine choice, training chunk size: plain data
+  if (d_params) c->d_params = d_params;
+  *out = c;
+  return ECNF_OK;
+}
+
 int ecnf_model_set_params(ecnf_model* m, const float* d_params) {
   if (!m) { ecnf_set_error("model is null"); return ECNF_ERR_INVALID; }
   m->d_params = d_params;

@@ -55,6 +55,7 @@ SIGNATURES = {
     "ecnf_model_create": (C.c_int, [C.POINTER(Config), _P, C.POINTER(_P)]),
     "ecnf_model_destroy": (None, [_P]),
     "ecnf_model_set_params": (C.c_int, [_P, _P]),
+    "ecnf_model_clone": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "ecnf_model_param_count": (_I64, [_P]),
     "ecnf_model_num_tensors": (C.c_int, [_P]),
     "ecnf_model_param_layout": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(_I64), C.POINTER(_I64),

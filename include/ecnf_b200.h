@@ -57,6 +57,11 @@ int ecnf_version(void);
 int ecnf_model_create(const ecnf_config* cfg, const float* d_params, ecnf_model** out);
 void ecnf_model_destroy(ecnf_model* m);
 int ecnf_model_set_params(ecnf_model* m, const float* d_params);
+/* A second handle with the same hyper-parameters and per-handle attributes (engine choice, training chunk size) bound to
+ * another parameter buffer (NULL: the same one).  Host-side and cheap (no device work, no allocation on the device): the
+ * way to pass the parameters PER CALL -- an XLA FFI handler clones the template handle with the call's parameter buffer,
+ * launches, and destroys the clone (kernel arguments are copied at launch), so concurrent calls never share mutable state. */
+int ecnf_model_clone(const ecnf_model* m, const float* d_params, ecnf_model** out);
 int64_t ecnf_model_param_count(const ecnf_model* m);   /* floats, incl. alignment padding */
 int ecnf_model_num_tensors(const ecnf_model* m);
 /* idx-th tensor: flax path ("EGNN_0/0/phi_e/Dense_0/kernel"), float offset, shape (cols==0 => vector/scalar). */

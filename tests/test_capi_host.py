@@ -109,3 +109,44 @@ def test_per_handle_attributes_fm_chunk_and_engine():
     assert lib.ecnf_model_set_engine(a.handle, 7) == -1
     with pytest.raises(L.EcnfError):
         a.set_engine(2)
+
+
+def test_model_clone_binds_other_parameters_without_touching_the_original():
+    """ecnf_model_clone: the per-call parameter binding an XLA FFI handler uses (clone -> launch -> destroy)."""
+    lib = L.load()
+    eng = Engine(CnfConfig(22, 3, 1e-6, 0.2, 3, (64, 64), 32, 8, 22))
+    eng.set_engine(1)
+    eng.set_fm_chunk(7)
+    h = C.c_void_p()
+    assert lib.ecnf_model_clone(eng.handle, None, C.byref(h)) == 0 and h.value and h.value != eng.handle
+    try:
+        assert lib.ecnf_model_param_count(h) == eng.param_count
+        assert lib.ecnf_fm_workspace_bytes(h, 100) == lib.ecnf_fm_workspace_bytes(eng.handle, 100)     # same chunk size
+        assert lib.ecnf_solve_tensor_flops_per_eval(h) == 0                                             # same engine choice (SIMT)
+        assert lib.ecnf_model_set_engine(h, 0) == 0                                                     # the clone's own attribute
+        assert lib.ecnf_solve_tensor_flops_per_eval(h) > 0 and lib.ecnf_solve_tensor_flops_per_eval(eng.handle) == 0
+    finally:
+        lib.ecnf_model_destroy(h)
+    assert lib.ecnf_model_clone(None, None, C.byref(h)) == -1
+
+
+def test_jax_ffi_shim_typechecks_against_the_c_abi():
+    """integration/jax_ffi/ecnf_jax_ffi.cc cannot be built here (no jaxlib headers); against a minimal stand-in of
+    xla/ffi/api/ffi.h every call it makes into include/ecnf_b200.h must still type-check, and every handler the Python
+    side registers must be defined."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    src = os.path.join(ROOT, "integration", "jax_ffi", "ecnf_jax_ffi.cc")
+    cuda_inc = "/usr/local/cuda/include"
+    r = subprocess.run([gxx, "-fsyntax-only", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "tests", "mock_xla"),
+                        "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    py = open(os.path.join(ROOT, "integration", "jax_ffi", "ecnf_jax.py")).read()
+    symbols = set(re.findall(r'"(Ecnf[A-Za-z]+)"', py))
+    assert len(symbols) == 11
+    for s in symbols:
+        assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({s}," in text, s
