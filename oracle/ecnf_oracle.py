@@ -3,11 +3,15 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this
 module.  The product path (``ecnf_b200``) never does: it fails loudly when the CUDA library is missing.
 
-PARITY UNPINNED: the reference (``/root/reference``) is pure Python/JAX and needs jax, flax, diffrax,
-distrax, e3nn_jax and optax, none of which exist in this image, and its own tests pin no values
-(``ecnf/cnf/core_test.py:42-43`` asserts nothing, ``ecnf/nets/egnn_test.py:31`` checks equivariance
-only).  This file is therefore a *restatement* of the reference written from its sources, validated by
-analytic known-answer tests (``tests/test_oracle_*.py``), not by outputs of the reference itself.
+PARITY: the reference (``/root/reference``) is pure Python/JAX and needs jax, flax, diffrax, distrax, e3nn_jax and
+optax, none of which exist in this image, and its own tests pin no values (``ecnf/cnf/core_test.py:42-43`` asserts
+nothing, ``ecnf/nets/egnn_test.py:31`` checks equivariance only).  This file is a *restatement* of the reference written
+from its sources.  It is PINNED to vectors produced by the reference's own source files executed over minimal stand-ins
+of their dependencies (``tests/golden/refshim``, ``tests/golden/make_refsrc_golden.py`` -> ``tests/golden/refsrc_*.npz``,
+checked by ``tests/test_refsrc_golden.py``): parameter tree, vector field, exact and Hutchinson divergences, base
+distribution, flow-matching loss, every gradient, update bookkeeping, solver call-site arguments.  It stays UNPINNED for
+the diffrax solver (``dopri5`` below: restated from the published algorithm) and optax's Adam (``adam_step``), which are
+validated by analytic known-answer tests only (``tests/test_oracle_kat.py``).
 
 Everything is written in torch on the CPU with an explicit dtype (float32 = like-for-like with the
 reference, float64 = ground truth) so that autograd can supply the reverse-mode Jacobian exactly as the
