@@ -22,6 +22,8 @@ Recorded per case (suffix _f32 = the float32 run, otherwise float64):
                         fixed-step branch's y0, quirk C#2)
   sc_*                  sample_cnf (:11-38): x0 = cnf.sample_base(key, 1)[0] and the call-site arguments
   base_*                cnf.sample_base(key, n), cnf.log_prob_base(x)   (build_cnf.py:46-61, zero_com_base.py)
+  lj_logp, dw_logp      the LJ / DW target log-densities of `energy_x` (leonard_jones.py:10-27, double_well.py:9-19)
+  forward_ess           calculate_forward_ess(ess_log_w, ess_mask)      (utils/evaluation.py:10-22)
   fm_*                  flow_matching_loss_fn (loss.py:10-32) through jax.value_and_grad: x0, t (its own draws), loss, every gradient
                         (stored in float32; LJ13 keeps block 1 and the top-level tensors only)
   upd_*                 flow_matching_update_fn (gradient_step.py:20-53) with a caller-supplied linear `opt_update`: key
@@ -47,6 +49,8 @@ from ecnf.cnf.build_cnf import build_cnf  # noqa: E402  (the reference)
 from ecnf.cnf.loss import flow_matching_loss_fn  # noqa: E402
 from ecnf.cnf.gradient_step import flow_matching_update_fn, TrainingState  # noqa: E402
 from ecnf.cnf.sample_and_log_prob import sample_cnf, get_log_prob, sample_and_log_prob_cnf  # noqa: E402
+from ecnf.targets.target_energy import leonard_jones, double_well  # noqa: E402
+from ecnf.utils.evaluation import calculate_forward_ess  # noqa: E402
 
 CASES = {
     "dw4": dict(n_frames=4, dim=2, sigma_min=0.01, base_scale=1.0, n_blocks_egnn=3, mlp_units=(128, 128, 128),
@@ -193,6 +197,13 @@ def run_case(name, kw, dtype, masters):
     out["base_samples"] = to_np(cnf.sample_base(bkey, 5))
     out["base_logp"] = to_np(cnf.log_prob_base(x))
 
+    # ---- target log-densities and the forward ESS (leonard_jones.py:10-27, double_well.py:9-19, utils/evaluation.py:10-22)
+    xe = torch.tensor(rng.standard_normal((B + 2, n, dim)) * 0.9 + 0.3, dtype=dtype)
+    out.update(energy_x=to_np(xe), lj_logp=to_np(leonard_jones.log_prob_fn(xe)), dw_logp=to_np(double_well.log_prob_fn(xe)))
+    log_w = torch.tensor(rng.standard_normal(64) * 2.0 - 30.0, dtype=dtype)
+    mask = torch.tensor((rng.uniform(0, 1, 64) < 0.8).astype(np.int64))
+    out.update(ess_log_w=to_np(log_w), ess_mask=to_np(mask), forward_ess=to_np(calculate_forward_ess(log_w, mask)["forward_ess"]))
+
     # ---- flow-matching loss and its gradient
     x_data = rng.standard_normal((B, n, dim))
     x_data = torch.tensor((x_data - x_data.mean(axis=1, keepdims=True)).reshape(B, D), dtype=dtype)
@@ -231,7 +242,7 @@ def main():
         r32, _ = run_case(name, kw, torch.float32, masters)
         out = dict(r64)
         for k in ("f", "div", "lp_exact_div", "lp_hutch_div", "sl_x0", "sl_logp_base", "sl_hutch_div", "base_samples", "base_logp",
-                  "fm_x0", "fm_t", "fm_loss", "upd_loss", "upd_grad_norm"):
+                  "fm_x0", "fm_t", "fm_loss", "upd_loss", "upd_grad_norm", "lj_logp", "dw_logp"):
             out[k + "_f32"] = r32[k]
         out.update({"param:" + p: v.astype(np.float32) for p, v in masters.items()})
         # gradients are stored in float32 (the fixtures stay a few MB); the big LJ13 case keeps block 1 and the top-level tensors

@@ -47,7 +47,7 @@ def squeeze(x, axis=None): return _t.squeeze(x) if axis is None else _t.squeeze(
 def repeat(x, repeats, axis=None): return _t.repeat_interleave(x, repeats, dim=axis)
 def sum(x, axis=None, keepdims=False): return _t.sum(x) if axis is None else _t.sum(x, dim=axis, keepdim=keepdims)
 def mean(x, axis=None, keepdims=False): return _t.mean(x) if axis is None else _t.mean(x, dim=axis, keepdim=keepdims)
-def where(c, a, b): return _t.where(c, a, b)
+def where(c, a, b): return _t.where(c if c.dtype == _t.bool else c != 0, a, b)      # jnp accepts a non-boolean condition
 def sqrt(x): return _t.sqrt(_f(x))
 def log(x): return _t.log(_f(x))
 def exp(x): return _t.exp(_f(x))

@@ -105,6 +105,17 @@ def test_oracle_base_distribution_and_key_reuse(path, f64_frequencies):
     assert np.abs(x0[0] - g["sc_x0"]).max() < 1e-6
 
 
+@pytest.mark.parametrize("path", FILES)
+def test_oracle_target_energies_and_forward_ess(path):
+    """leonard_jones.py:10-27, double_well.py:9-19 (log p = -E) and utils/evaluation.py:10-22."""
+    g = np.load(path, allow_pickle=False)
+    x = g["energy_x"]
+    assert np.abs(-O.lj_energy(x) - g["lj_logp"]).max() < 1e-9 * np.abs(g["lj_logp"]).max()
+    assert np.abs(-O.dw_energy(x) - g["dw_logp"]).max() < 1e-9 * np.abs(g["dw_logp"]).max()
+    fe = O.forward_ess(g["ess_log_w"], g["ess_mask"].astype(bool))
+    assert abs(fe - float(g["forward_ess"])) < 1e-10 * float(g["forward_ess"])
+
+
 @pytest.mark.parametrize("path", FILES[:1])
 def test_solver_call_sites_of_the_reference(path):
     """The arguments the reference passes to diffeqsolve (captured from its own calls): what the on-device loop mirrors."""
@@ -174,6 +185,11 @@ def test_cuda_matches_the_reference_source(path, cuda_device):
     assert np.abs(eng.base_log_prob(torch.tensor(x)).cpu().numpy() - g["base_logp"]).max() < 1e-4 * (1 + np.abs(g["base_logp"]).max())
     eps = torch.tensor(g["sl_eps"].astype(np.float32))
     assert np.abs(eng.base_sample_from_noise(eps).cpu().numpy() - g["sl_x0"]).max() < 1e-6
+    from ecnf_b200 import lib as L
+    xe = torch.tensor(g["energy_x"].astype(np.float32)).reshape(g["energy_x"].shape[0], -1)
+    for kind, key, tol in ((L.TARGET_LJ, "lj_logp", 1e-4), (L.TARGET_DW, "dw_logp", 2e-5)):
+        got = eng.target_log_prob(kind, xe).cpu().numpy()
+        assert np.abs(got - g[key]).max() < tol * np.abs(g[key]).max(), key
     loss, grad = eng.fm_loss_grad(tree, g["x_data"].astype(np.float32), g["fm_x0"].astype(np.float32), g["fm_t"].astype(np.float32), feat)
     assert abs(float(loss[0]) - float(g["fm_loss"])) < 1e-5 * abs(float(g["fm_loss"]))
     mine = O.nested_to_flat(eng.unpack(grad, to_numpy=True)["params"])
