@@ -199,3 +199,32 @@ def test_cuda_matches_the_reference_source(path, cuda_device):
             assert np.abs(mine[k]).max() == 0.0, k          # dead parameters of the last block: exact zeros on both sides
         else:
             assert np.abs(mine[k] - v).max() < 1e-4 * scale, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES)
+def test_facade_is_key_for_key_the_reference(path, cuda_device):
+    """The reference-shaped Python API given the SAME jax-style keys as the reference's own code: same base draws, same base
+    log-densities, same flow-matching loss (loss.py:21-24 draws included), same update bookkeeping."""
+    from ecnf_b200.cnf import build_cnf, flow_matching_loss_fn, flow_matching_update_fn, TrainingState
+    from ecnf_b200.utils.optim import Adam
+    g, kw, cfg, flat, grads = _load(path)
+    cnf = build_cnf(**kw)
+    tree = O.flat_to_nested({k: v.astype(np.float32) for k, v in flat.items()})
+    feat = g["feat"].astype(np.int32)
+    assert np.abs(cnf.sample_base(g["base_key"], 5).cpu().numpy() - g["base_samples"]).max() < 1e-6
+    assert np.abs(cnf.log_prob_base(torch.tensor(g["x"].astype(np.float32))).cpu().numpy() - g["base_logp"]).max() \
+        < 1e-4 * (1 + np.abs(g["base_logp"]).max())
+    x0, lp0 = cnf.sample_and_log_prob_base(g["keys"][0], ())
+    assert np.abs(x0.cpu().numpy() - g["sl_x0"][0]).max() < 1e-6
+    assert abs(float(lp0) - float(g["sl_logp_base"][0])) < 1e-4 * (1 + abs(float(g["sl_logp_base"][0])))
+    loss, info = flow_matching_loss_fn(cnf, tree, g["x_data"].astype(np.float32), g["fm_key"], feat)
+    assert abs(float(loss) - float(g["fm_loss"])) < 1e-5 * abs(float(g["fm_loss"]))
+    # one update step: the new key and the loss (drawn from the sub-key) are the reference's
+    opt = Adam(1e-4)
+    params = cnf.engine.pack(tree)
+    state = TrainingState(params=params, opt_state=opt.init(params), key=g["upd_key_in"], ema_params=params)
+    new_state, uinfo = flow_matching_update_fn(cnf, opt.update, state, g["x_data"].astype(np.float32), feat)
+    assert (np.asarray(new_state.key) == g["upd_key_out"]).all()
+    assert abs(float(uinfo["loss"]) - float(g["upd_loss"])) < 1e-5 * abs(float(g["upd_loss"]))
+    assert abs(float(uinfo["grad_norm"]) - float(g["upd_grad_norm"])) < 1e-4 * float(g["upd_grad_norm"])
