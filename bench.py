@@ -571,7 +571,7 @@ def main():
     if args.workload == "lj13":
         b0, b1 = rng_for(10_000, 10_000)
         r = bench_solve(c, "lj13", b0, b1, div=True, adaptive=args.adaptive, steps=args.steps, warmup=args.warmup,
-                        target=L.TARGET_LJ, e2e_steps=max(1, min(args.steps, 3)), sample_clocks=True, count=not args.no_count)
+                        target=L.TARGET_LJ, e2e_steps=max(1, min(args.steps, 5)), sample_clocks=True, count=not args.no_count)
         extra = {"reverse_ess": r.get("reverse_ess"), "forward_ess": r.get("forward_ess"), "step_ms": r["step_ms"],
                  "kernels_per_step": r.get("kernels_per_step"), "status_failures": r["status_failures"]}
         launches = r["launches_per_step"] * args.steps
