@@ -148,11 +148,22 @@ def apply(cnf: Cnf, params, x, t, features):
         pack(cnf, params), x, t, features.astype(jnp.int32), ws, model=np.int64(cnf.handle))
 
 
+def _from_noise(cnf: Cnf, eps):
+    """x0 = base_scale * remove_mean(eps) for a batch of raw normal draws [B, D] (zero_com_base.py:44-47, 88-93)."""
+    return jax.ffi.ffi_call("ecnf_base_sample_from_noise", jax.ShapeDtypeStruct(eps.shape, jnp.float32))(
+        eps, model=np.int64(cnf.handle))
+
+
 def sample_base(cnf: Cnf, key, n: int):
-    """cnf.sample_base(key, n)  (build_cnf.py:46-48, zero_com_base.py:44-47): the draw stays jax.random's."""
-    eps = jax.random.normal(key, (n, cnf.D), jnp.float32)
-    return jax.ffi.ffi_call("ecnf_base_sample_from_noise", jax.ShapeDtypeStruct((n, cnf.D), jnp.float32))(
-        eps, model=np.int64(cnf.handle)), eps
+    """cnf.sample_base(key, n)  (build_cnf.py:46-48): the draw stays jax.random's; returns (x0 [n, D], raw noise)."""
+    eps = jax.random.normal(key, (n, cnf.n_frames, cnf.dim), jnp.float32).reshape(n, cnf.D)
+    return _from_noise(cnf, eps), eps
+
+
+def _per_key_base(cnf: Cnf, keys):
+    """vmap over keys of cnf.sample_base(key, 1)[0]: the draws are vmapped (pure jax), the library is called once."""
+    eps = jax.vmap(lambda k: jax.random.normal(k, (1, cnf.n_frames, cnf.dim), jnp.float32).reshape(cnf.D))(keys)
+    return _from_noise(cnf, eps), eps
 
 
 def log_prob_base(cnf: Cnf, x):
@@ -162,7 +173,7 @@ def log_prob_base(cnf: Cnf, x):
 
 def sample_cnf(cnf: Cnf, params, keys, features, use_fixed_step_size=False, rtol=1e-5, atol=1e-5, step_size=0.05):
     """sample_and_log_prob.py:11-38, vmapped over the leading axis of `keys` [B, 2] / `features` [B, n]."""
-    x0 = jax.vmap(lambda k: sample_base(cnf, k, 1)[0][0])(keys)
+    x0, _ = _per_key_base(cnf, keys)
     x1, _, stats = _solve(cnf, L.MODE_SAMPLE, pack(cnf, params), x0, features, _ctrl(use_fixed_step_size, rtol, atol, step_size))
     return x1
 
@@ -179,7 +190,7 @@ def sample_and_log_prob_cnf(cnf: Cnf, params, keys, features, approx=False, use_
                             atol=1e-5, step_size=0.05):
     """sample_and_log_prob.py:97-149: (x1, log_q).  approx=True reuses the base-sample key for the probe like the reference
     (:130,137: the same key gives the same normal draw, so eps is the raw noise underneath x0)."""
-    x0, raw = jax.vmap(lambda k: tuple(a[0] for a in sample_base(cnf, k, 1)))(keys)
+    x0, raw = _per_key_base(cnf, keys)
     x1, logs, _ = _solve(cnf, L.MODE_SAMPLE_LOGQ, pack(cnf, params), x0, features,
                          _ctrl(use_fixed_step_size, rtol, atol, step_size), raw if approx else None)
     return x1, logs[:, 0]
